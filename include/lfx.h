@@ -1,0 +1,246 @@
+/*
+ * lfx.h — C ABI of the B200-native LiDAR feature extraction path.
+ *
+ * Drop-in boundary for ONE path of tier4/lidar_feature_extraction: the body of
+ * FeatureExtraction::Callback (extraction/app/feature_extraction.cpp:92-171), i.e. lines 110-157
+ * (ring extraction, curvature, labelling, masks, edge/surface gathering) plus the PointXYZ
+ * conversion of lines 163-164. Everything is `extern "C"`, plain pointers and sizes; no C++ or
+ * torch types cross this boundary. INTEGRATION.md shows the rclcpp-side stub that calls it.
+ *
+ * All "replaces" citations are file:line under the reference repository.
+ *
+ * The implementation is CUDA-only (sm_100a). There is no CPU fallback: without a usable device
+ * lfx_create() fails with LFX_E_CUDA.
+ */
+#ifndef LFX_H_
+#define LFX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFX_VERSION_MAJOR 0
+#define LFX_VERSION_MINOR 1
+
+/* ------------------------------------------------------------------ status codes
+ * The reference signals these conditions by RCLCPP_ERROR + rclcpp::shutdown()
+ * (feature_extraction.cpp:96-108) or asserts (hyper_parameter.hpp:45-53). */
+enum {
+  LFX_OK = 0,
+  LFX_E_BAD_PARAM = 1,  /* hyper_parameter.hpp:45-53 asserts; or outside the supported envelope */
+  LFX_E_NOT_DENSE = 2,  /* feature_extraction.cpp:96-101 */
+  LFX_E_NO_RING = 3,    /* feature_extraction.cpp:103-108, RingIsAvailable ring.cpp:36-44 */
+  LFX_E_BAD_LAYOUT = 4, /* PointCloud2 view that pcl::fromROSMsg could not map either */
+  LFX_E_CAPACITY = 5,   /* a ring longer than max_ring_points / ring id >= max_rings (see lfx_options) */
+  LFX_E_CUDA = 6,
+  LFX_E_STATE = 7       /* call order violated (e.g. fetch before extract) */
+};
+
+/* ------------------------------------------------------------------ labels
+ * PointLabel, extraction/include/lidar_feature_extraction/point_label.hpp:32-42. */
+enum {
+  LFX_LABEL_DEFAULT = 0,
+  LFX_LABEL_EDGE = 1,
+  LFX_LABEL_EDGE_NEIGHBOR = 2,
+  LFX_LABEL_SURFACE = 3,
+  LFX_LABEL_SURFACE_NEIGHBOR = 4,
+  LFX_LABEL_OUT_OF_RANGE = 5,
+  LFX_LABEL_OCCLUDED = 6,
+  LFX_LABEL_PARALLEL_BEAM = 7,
+  LFX_LABEL_NONE = 255 /* point of a ring that contributes nothing (sparse or skipped, see below) */
+};
+
+/* per-ring status in lfx_ring_info */
+enum {
+  LFX_RING_OK = 0,
+  LFX_RING_SPARSE = 1,  /* fewer than padding+1 points: RemoveSparseRings, ring.cpp:46-59 */
+  LFX_RING_SKIPPED = 2, /* the reference would throw std::invalid_argument and WARN,
+                           feature_extraction.cpp:154-156 (too short for the convolution / sectors,
+                           or two adjacent points with zero XY norm, math.cpp:40-42) */
+  LFX_RING_TOO_LONG = 3 /* exceeds lfx_options.max_ring_points: reported as LFX_E_CAPACITY */
+};
+
+/* ------------------------------------------------------------------ parameters
+ * Replaces HyperParameters (hyper_parameter.hpp:32-65): same nine fields, same meaning.
+ * ROS parameter names: convolution_padding, neighbor_degree_threshold, distance_diff_threshold,
+ * parallel_beam_min_range_ratio, edge_threshold, surface_threshold, min_range, max_range, n_blocks. */
+typedef struct lfx_params {
+  int padding;
+  double neighbor_degree_threshold;
+  double distance_diff_threshold;
+  double parallel_beam_min_range_ratio;
+  double edge_threshold;
+  double surface_threshold;
+  double min_range;
+  double max_range;
+  int n_blocks;
+} lfx_params;
+
+/* compiled defaults, hyper_parameter.hpp:35-43 */
+void lfx_default_params(lfx_params *out);
+/* deployed set, lidar_feature_launch/config/lidar_feature_extraction.param.yaml:3-10 */
+void lfx_launch_yaml_params(lfx_params *out);
+
+/* Sizing and diagnostics knobs that have no counterpart in the reference. Zero = default. */
+typedef struct lfx_options {
+  int device;            /* CUDA device ordinal */
+  int max_ring_points;   /* longest ring held on chip; default 2304, max 8192 */
+  int max_rings;         /* ring ids must be < max_rings; default 128, max 4096 */
+  int want_sorted_src;   /* also produce the ring-sorted -> source index map (4 B/point) */
+  int want_curvature;    /* also produce per-point curvature, f64 (8 B/point; test/diagnostic mode) */
+  int force_order_path;  /* testing: 0 auto, 1 force key sort, 2 force exact comparator sort */
+  void *stream;          /* cudaStream_t to enqueue on; NULL = a stream owned by the handle */
+  int use_graph;         /* 1 (default when 0 is passed with graph_default) capture batches in CUDA graphs; -1 disables */
+} lfx_options;
+
+/* ------------------------------------------------------------------ input
+ * Replaces GetPointCloud<PointXYZIR>(PointCloud2) (lib/include/lidar_feature_library/ros_msg.hpp:73-79,
+ * point_type.hpp:62-86): fields are located by the caller (by name, as pcl::fromROSMsg does) and
+ * passed as byte offsets. Deployed layout (point_type_converter/convert.py:134-145): point_step 32,
+ * x@0 y@4 z@8 intensity@16 (f32), ring@20 (u16). Points need not be organised or ring-ordered. */
+enum { LFX_MEM_HOST = 0, LFX_MEM_DEVICE = 1 };
+enum { LFX_RING_U8 = 2, LFX_RING_U16 = 4, LFX_RING_U32 = 6 }; /* sensor_msgs/PointField datatype ids */
+
+typedef struct lfx_cloud_view {
+  const void *data;       /* PointCloud2.data */
+  uint32_t n_points;      /* width * height */
+  uint32_t point_step;
+  uint32_t off_x, off_y, off_z, off_ring;
+  uint8_t ring_datatype;  /* LFX_RING_U16 in the deployed layout */
+  uint8_t has_ring;       /* 0 => LFX_E_NO_RING */
+  uint8_t is_dense;       /* 0 => LFX_E_NOT_DENSE */
+  uint8_t memory;         /* LFX_MEM_HOST (pageable or pinned) or LFX_MEM_DEVICE */
+} lfx_cloud_view;
+
+/* ------------------------------------------------------------------ results */
+typedef struct lfx_ring_info {
+  uint32_t count;       /* points carrying this ring id */
+  uint32_t offset;      /* first position of the ring inside its scan's ring-sorted arrays */
+  uint32_t n_edge;
+  uint32_t n_surface;
+  uint32_t status;      /* LFX_RING_* */
+  uint32_t order_path;  /* diagnostics: 0 rotated-monotone, 1 key sort, 2 exact comparator sort */
+} lfx_ring_info;
+
+/* Device-side view of the last batch. Pointers stay valid until the next lfx_extract_batch /
+ * lfx_destroy on the handle. All arrays are on the handle's device.
+ *
+ * Feature clouds replace what the reference publishes on scan_edge / scan_surface after
+ * ToPointXYZ (feature_extraction.cpp:163-166): 16-byte points x,y,z,1.0f (pcl::PointXYZ layout).
+ * Within a scan: rings ascending by id, inside a ring ascending sorted index
+ * (GetIndicesByValue, lib/include/lidar_feature_library/algorithm.hpp:50-62). Scans concatenated
+ * in batch order; scan s owns [offsets[2s], offsets[2s]+counts[2s]) of edge_xyz and
+ * [offsets[2s+1], ...+counts[2s+1]) of surface_xyz. */
+typedef struct lfx_batch_result {
+  int n_scans;
+  uint64_t total_points;
+  const float *d_edge_xyz;        /* [sum n_edge][4] */
+  const float *d_surface_xyz;     /* [sum n_surface][4] */
+  const uint32_t *d_counts;       /* [n_scans][2]   (n_edge, n_surface) */
+  const uint32_t *d_offsets;      /* [n_scans+1][2] exclusive prefix of d_counts (last row = totals) */
+  const uint8_t *d_labels;        /* [total_points] final PointLabel per point in ring-sorted order */
+  const uint32_t *d_sorted_src;   /* [total_points] or NULL: source index inside the scan */
+  const double *d_curvature;      /* [total_points] or NULL */
+  const lfx_ring_info *d_rings;   /* [n_scans][max_rings] */
+  const uint64_t *d_point_base;   /* [n_scans+1] first position of each scan in the per-point arrays */
+  int max_rings;
+} lfx_batch_result;
+
+typedef struct lfx_handle lfx_handle;
+
+/* ------------------------------------------------------------------ lifecycle */
+/* Replaces the FeatureExtraction node's constructor state (feature_extraction.cpp:65-88, 173-175):
+ * parameters are immutable after creation. */
+int lfx_create(const lfx_params *params, const lfx_options *options, lfx_handle **out);
+void lfx_destroy(lfx_handle *h);
+/* Human-readable description of the last non-OK status (h may be NULL for create failures). */
+const char *lfx_last_error(const lfx_handle *h);
+int lfx_get_params(const lfx_handle *h, lfx_params *out);
+int lfx_device(const lfx_handle *h);
+
+/* ------------------------------------------------------------------ extraction
+ * Replaces feature_extraction.cpp:110-157 + 163-164 for `n_scans` independent PointCloud2 messages
+ * (the callback is const and stateless, :92, so scans batch freely). Work is enqueued on the handle's
+ * stream; the call returns once everything is enqueued (host views are copied H2D asynchronously, so
+ * host buffers must stay valid until lfx_synchronize or a fetch). `out` may be NULL. */
+int lfx_extract_batch(lfx_handle *h, const lfx_cloud_view *scans, int n_scans, lfx_batch_result *out);
+int lfx_synchronize(lfx_handle *h);
+
+/* Per-batch status after completion: returns LFX_OK or LFX_E_CAPACITY (first offending scan/ring in
+ * lfx_last_error). Synchronises. */
+int lfx_batch_status(lfx_handle *h);
+
+/* D2H helpers (synchronise the handle's stream). Buffers are caller-owned.
+ * counts: [n_scans][2] u32; offsets: [n_scans+1][2] u32. */
+int lfx_fetch_counts(lfx_handle *h, uint32_t *counts, uint32_t *offsets);
+/* edge/surface: capacity in points (16 B each); copies the whole batch's concatenated clouds. */
+int lfx_fetch_features(lfx_handle *h, float *edge_xyz, size_t edge_capacity_points,
+                       float *surface_xyz, size_t surface_capacity_points);
+/* per-point arrays, total_points long each (NULL to skip). sorted_src / curvature need the
+ * corresponding lfx_options flag. */
+int lfx_fetch_points(lfx_handle *h, uint8_t *labels, uint32_t *sorted_src, double *curvature);
+int lfx_fetch_rings(lfx_handle *h, lfx_ring_info *rings /* [n_scans][max_rings] */);
+
+/* Convenience for a ROS-callback-shaped caller: one PointCloud2 in, two pcl::PointXYZ payloads out
+ * (pinned host memory owned by the handle, valid until the next call). Synchronous. */
+typedef struct lfx_scan_output {
+  const float *edge_xyz;     /* [n_edge][4] */
+  const float *surface_xyz;  /* [n_surface][4] */
+  uint32_t n_edge, n_surface;
+  const uint8_t *labels;     /* [n_points], ring-sorted order (source for colored_scan) */
+  const uint32_t *sorted_src;/* [n_points] or NULL */
+  uint32_t n_points;
+} lfx_scan_output;
+int lfx_extract_scan(lfx_handle *h, const lfx_cloud_view *scan, lfx_scan_output *out);
+
+/* LabelToColor, extraction/src/color_points.cpp:39-68 (colored_scan is derived on the host from
+ * the label bytes; it is a depth-1 debug topic, feature_extraction.cpp:77-78). rgb[3]. */
+int lfx_label_to_color(uint8_t label, uint8_t *rgb);
+
+/* ------------------------------------------------------------------ memory helpers */
+/* Pinned host memory so that H2D/D2H run at full PCIe speed. */
+void *lfx_host_alloc(size_t bytes);
+void lfx_host_free(void *p);
+int lfx_device_alloc(lfx_handle *h, size_t bytes, void **out);
+int lfx_device_free(lfx_handle *h, void *p);
+int lfx_memcpy_h2d(lfx_handle *h, void *dst_device, const void *src_host, size_t bytes);
+int lfx_memcpy_d2h(lfx_handle *h, void *dst_host, const void *src_device, size_t bytes);
+
+/* ------------------------------------------------------------------ instrumentation */
+/* Kernels launched / graph launches issued by this handle so far (bench.py's gpu_launches). */
+uint64_t lfx_kernel_launch_count(const lfx_handle *h);
+/* Device time of the last batch's stages, measured with CUDA events on the handle's stream:
+ * ms[0]=ingest(hist+plan+scatter) ms[1]=ring kernel ms[2]=pack. Only when timing was enabled. */
+int lfx_set_stage_timing(lfx_handle *h, int enabled);
+int lfx_last_stage_ms(lfx_handle *h, float *ms3);
+
+/* ------------------------------------------------------------------ synthetic scans
+ * Deterministic generator for the BASELINE.json sensor shapes (test/bench input, not part of the
+ * reference). Emits the deployed 32-byte layout in sensor firing order (azimuth-major, ring-minor,
+ * clockwise from a per-scan random start azimuth). */
+enum { LFX_WORLD_ROOM = 0, LFX_WORLD_TUNNEL = 1 };
+typedef struct lfx_synth_spec {
+  int n_rings, n_cols;
+  float elev_lo_deg, elev_hi_deg; /* ring 0 .. ring n_rings-1 */
+  int world;                      /* LFX_WORLD_* */
+  float range_noise;              /* metres, gaussian sigma */
+  float dropout_prob;             /* probability that a return is missing (points removed) */
+  float dropout_burst;            /* mean burst length in columns (>= 1) */
+  float near_prob;                /* probability of a spurious < min_range return */
+  uint64_t seed;
+} lfx_synth_spec;
+/* named shapes: "vlp16" 16x1800, "hdl32" 32x2170, "hdl64" 64x2048 (tunnel), "os128" 128x2048 */
+int lfx_synth_named(const char *name, lfx_synth_spec *out);
+/* host generator: out capacity n_rings*n_cols*32 bytes; writes actual point count */
+int lfx_synth_scan_host(const lfx_synth_spec *spec, uint64_t frame, void *out, uint32_t *n_points_out);
+/* device generator (no drop-outs): n_scans consecutive frames, each n_rings*n_cols*32 bytes, contiguous */
+int lfx_synth_batch_device(lfx_handle *h, const lfx_synth_spec *spec, uint64_t first_frame, int n_scans,
+                           void *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFX_H_ */

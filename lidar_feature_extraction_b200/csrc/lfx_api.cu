@@ -1,0 +1,795 @@
+// lfx_api.cu — host side of the C ABI declared in include/lfx.h.
+//
+// One handle = one GPU, one stream, grow-only device buffers, and a cache of CUDA graphs keyed by
+// the batch geometry (number of scans, number of ingest tiles). Parameters are frozen at creation
+// (the reference node holds `const HyperParameters params_`, feature_extraction.cpp:173); derived
+// constants (the cosine cut replacing acos(c) < theta) are computed here on the host with the same
+// libm the reference would use.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "lfx.h"
+#include "lfx_kernels.cuh"
+#include "lfx_synth.h"
+
+using namespace lfxk;
+
+namespace
+{
+
+thread_local std::string g_create_error;
+
+template<typename T>
+struct DevBuf
+{
+  T * p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+struct GraphKey
+{
+  int n_scans;
+  uint32_t n_tiles;
+  bool operator<(const GraphKey & o) const { return n_scans != o.n_scans ? n_scans < o.n_scans : n_tiles < o.n_tiles; }
+};
+
+}  // namespace
+
+struct lfx_handle
+{
+  lfx_params params{};
+  lfx_options opt{};
+  DevParams dev{};
+  int device = 0;
+  int num_sms = 0;
+  int ring_grid = 0, pack_grid = 0;
+  size_t ring_smem = 0;
+  int cap = 0, cap2 = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  uint64_t launches = 0;
+
+  // device buffers
+  DevBuf<ScanDesc> d_scans;
+  DevBuf<uint64_t> d_point_base;
+  DevBuf<uint16_t> d_ring16;
+  DevBuf<uint32_t> d_tile_hist;
+  DevBuf<lfx_ring_info> d_rings;
+  DevBuf<uint2> d_work;
+  DevBuf<uint2> d_ring_featoff;
+  DevBuf<uint32_t> d_idx;
+  DevBuf<uint8_t> d_labels;
+  DevBuf<uint32_t> d_sorted_src;
+  DevBuf<double> d_curv;
+  DevBuf<float4> d_stage, d_edge, d_surface;
+  DevBuf<uint32_t> d_counts, d_offsets;
+  DevBuf<uint8_t> d_input;
+  uint32_t * d_counters = nullptr;
+
+  // pinned host staging
+  ScanDesc * h_scans = nullptr;
+  uint64_t * h_point_base = nullptr;
+  size_t h_scans_cap = 0;
+  uint32_t * h_counters = nullptr;
+  // single-scan convenience mirrors
+  float4 * h_edge = nullptr, * h_surface = nullptr;
+  uint8_t * h_labels = nullptr;
+  uint32_t * h_sorted_src = nullptr;
+  size_t h_scan_cap = 0;
+
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+
+  // last batch
+  int n_scans = 0;
+  uint64_t total_points = 0;
+  uint32_t total_tiles = 0;
+  bool have_batch = false;
+
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool have_timing = false;
+};
+
+namespace
+{
+
+#define LFX_CUDA(h, call)                                                                          \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                              \
+      return LFX_E_CUDA;                                                                           \
+    }                                                                                              \
+  } while (0)
+
+int fail(lfx_handle * h, int code, const std::string & msg)
+{
+  h->err = msg;
+  return code;
+}
+
+template<typename T>
+int ensure(lfx_handle * h, DevBuf<T> & b, size_t n, bool * regrown)
+{
+  if (n <= b.cap) { return LFX_OK; }
+  // all work using the old buffer must be finished before it is released
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (b.p) { LFX_CUDA(h, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+  const size_t want = n + n / 8 + 64;
+  LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&b.p), want * sizeof(T)));
+  b.cap = want;
+  if (regrown) { *regrown = true; }
+  return LFX_OK;
+}
+
+void drop_graphs(lfx_handle * h)
+{
+  for (auto & kv : h->graphs) { cudaGraphExecDestroy(kv.second); }
+  h->graphs.clear();
+}
+
+// Smallest double c with acos(c) < theta; is_neighbor <=> c_min <= c <= 1.
+// acos is the host libm's, i.e. the one the reference itself calls (math.cpp:45).
+double cos_cut(double theta)
+{
+  auto key = [](double v) { int64_t b; memcpy(&b, &v, 8); return b < 0 ? (int64_t)(0x8000000000000000ull - (uint64_t)b) : b; };
+  auto unkey = [](int64_t k) { int64_t b = k < 0 ? (int64_t)(0x8000000000000000ull - (uint64_t)k) : k; double v; memcpy(&v, &b, 8); return v; };
+  if (!(std::acos(1.0) < theta)) { return 2.0; }       // nothing is ever a neighbour
+  if (std::acos(-1.0) < theta) { return -1.0; }        // everything with a finite cosine is
+  int64_t lo = key(-1.0), hi = key(1.0);               // pred(lo) false, pred(hi) true
+  while (hi - lo > 1) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (std::acos(unkey(mid)) < theta) { hi = mid; } else { lo = mid; }
+  }
+  return unkey(hi);
+}
+
+int next_pow2(int v) { int p = 32; while (p < v) { p <<= 1; } return p; }
+
+int validate_params(const lfx_params & p, std::string & why)
+{
+  // hyper_parameter.hpp:45-53: everything strictly positive
+  if (!(p.padding > 0) || !(p.neighbor_degree_threshold > 0) || !(p.distance_diff_threshold > 0) ||
+      !(p.parallel_beam_min_range_ratio > 0) || !(p.edge_threshold > 0) || !(p.surface_threshold > 0) ||
+      !(p.min_range > 0) || !(p.max_range > 0) || !(p.n_blocks > 0)) {
+    why = "all nine parameters must be > 0 (hyper_parameter.hpp:45-53)";
+    return LFX_E_BAD_PARAM;
+  }
+  if (p.padding > MAX_PADDING) { why = "convolution_padding > 15 is outside the supported envelope"; return LFX_E_BAD_PARAM; }
+  if (p.n_blocks > MAX_BLOCKS) { why = "n_blocks > 64 is outside the supported envelope"; return LFX_E_BAD_PARAM; }
+  return LFX_OK;
+}
+
+// ---- the batch pipeline (enqueued on h->stream; also the body of the captured graph)
+int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_events)
+{
+  const int max_rings = h->opt.max_rings;
+  LFX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * C_COUNT, h->stream));
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[0], h->stream)); }
+  if (n_tiles > 0) {
+    k_ring_hist<<<n_tiles, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
+      h->d_scans.p, n_scans, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
+  }
+  k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
+    h->d_scans.p, h->d_tile_hist.p, h->d_rings.p, h->d_work.p, h->d_counters, max_rings, h->params.padding, h->cap);
+  if (n_tiles > 0) {
+    k_ring_scatter<<<n_tiles, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
+      h->d_scans.p, n_scans, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
+  }
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[1], h->stream)); }
+  RingArgs ra;
+  ra.scans = h->d_scans.p;
+  ra.idx = h->d_idx.p;
+  ra.rings = h->d_rings.p;
+  ra.work = h->d_work.p;
+  ra.counters = h->d_counters;
+  ra.labels = h->d_labels.p;
+  ra.sorted_src = h->opt.want_sorted_src ? h->d_sorted_src.p : nullptr;
+  ra.curvature = h->opt.want_curvature ? h->d_curv.p : nullptr;
+  ra.stage = h->d_stage.p;
+  ra.max_rings = max_rings;
+  ra.cap = h->cap;
+  ra.cap2 = h->cap2;
+  ra.force_order_path = h->opt.force_order_path;
+  ra.prm = h->dev;
+  k_extract_rings<<<h->ring_grid, RING_THREADS, h->ring_smem, h->stream>>>(ra);
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
+  k_feat_offsets_a<<<n_scans, 128, 0, h->stream>>>(h->d_rings.p, h->d_ring_featoff.p, h->d_counts.p, max_rings);
+  k_feat_offsets_b<<<1, 1024, 0, h->stream>>>(h->d_counts.p, h->d_offsets.p, n_scans);
+  k_pack_copy<<<h->pack_grid, 256, 0, h->stream>>>(
+    h->d_work.p, h->d_counters, h->d_scans.p, h->d_rings.p, h->d_ring_featoff.p, h->d_offsets.p, h->d_stage.p,
+    h->d_edge.p, h->d_surface.p, max_rings);
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[3], h->stream)); }
+  LFX_CUDA(h, cudaGetLastError());
+  return LFX_OK;
+}
+
+constexpr int KERNELS_PER_BATCH = 7;
+
+}  // namespace
+
+// ====================================================================== C ABI
+
+extern "C" {
+
+void lfx_default_params(lfx_params * out)
+{
+  // hyper_parameter.hpp:35-43
+  out->padding = 5;
+  out->neighbor_degree_threshold = 2.0;
+  out->distance_diff_threshold = 0.3;
+  out->parallel_beam_min_range_ratio = 0.02;
+  out->edge_threshold = 0.05;
+  out->surface_threshold = 0.05;
+  out->min_range = 0.1;
+  out->max_range = 100.0;
+  out->n_blocks = 6;
+}
+
+void lfx_launch_yaml_params(lfx_params * out)
+{
+  // lidar_feature_launch/config/lidar_feature_extraction.param.yaml:3-10; surface_threshold is not
+  // in the YAML and keeps its compiled default
+  lfx_default_params(out);
+  out->padding = 2;
+  out->neighbor_degree_threshold = 3.0;
+  out->distance_diff_threshold = 0.3;
+  out->parallel_beam_min_range_ratio = 0.02;
+  out->edge_threshold = 50.0;
+  out->min_range = 0.1;
+  out->max_range = 1000.0;
+  out->n_blocks = 6;
+}
+
+const char * lfx_last_error(const lfx_handle * h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handle ** out)
+{
+  if (!params || !out) { g_create_error = "null argument"; return LFX_E_BAD_PARAM; }
+  *out = nullptr;
+  std::string why;
+  if (int rc = validate_params(*params, why)) { g_create_error = why; return rc; }
+  lfx_handle * h = new lfx_handle();
+  h->params = *params;
+  if (options) { h->opt = *options; }
+  if (h->opt.max_ring_points <= 0) { h->opt.max_ring_points = 2304; }
+  if (h->opt.max_rings <= 0) { h->opt.max_rings = 128; }
+  if (h->opt.max_ring_points > 8192 || h->opt.max_rings > 4096 || h->opt.force_order_path < 0 || h->opt.force_order_path > 2) {
+    g_create_error = "lfx_options outside the supported envelope (max_ring_points <= 8192, max_rings <= 4096)";
+    delete h;
+    return LFX_E_BAD_PARAM;
+  }
+  h->device = h->opt.device;
+  h->cap = (std::max(h->opt.max_ring_points, 2 * params->padding + 2) + 63) & ~63;
+  h->cap2 = next_pow2(h->cap);
+
+  auto bail = [&](cudaError_t e, const char * what) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    lfx_destroy(h);
+    return LFX_E_CUDA;
+  };
+  cudaError_t e;
+  int n_dev = 0;
+  if ((e = cudaGetDeviceCount(&n_dev)) != cudaSuccess || n_dev == 0) {
+    g_create_error = std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+    delete h;
+    return LFX_E_CUDA;
+  }
+  if ((e = cudaSetDevice(h->device)) != cudaSuccess) { return bail(e, "cudaSetDevice"); }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) { return bail(e, "cudaGetDeviceProperties"); }
+  h->num_sms = prop.multiProcessorCount;
+  if (h->opt.stream) { h->stream = reinterpret_cast<cudaStream_t>(h->opt.stream); }
+  else {
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { return bail(e, "cudaStreamCreate"); }
+    h->own_stream = true;
+  }
+
+  // derived constants
+  h->dev.P = params->padding;
+  h->dev.B = params->n_blocks;
+  h->dev.c_min = cos_cut(params->neighbor_degree_threshold * M_PI / 180.0);  // DegreeToRadian degree_to_radian.hpp:34-37
+  h->dev.d = params->distance_diff_threshold;
+  h->dev.rho = params->parallel_beam_min_range_ratio;
+  h->dev.tau_e = params->edge_threshold;
+  h->dev.tau_s = params->surface_threshold;
+  h->dev.rmin = params->min_range;
+  h->dev.rmax = params->max_range;
+  h->dev.center_w = -2. * params->padding;  // MakeWeight curvature.cpp:40
+
+  // kernel attributes / persistent grid sizes
+  h->ring_smem = ring_smem_bytes(h->cap, h->cap2);
+  if (h->ring_smem > (size_t)prop.sharedMemPerBlockOptin) {
+    g_create_error = "max_ring_points does not fit in shared memory";
+    lfx_destroy(h);
+    return LFX_E_BAD_PARAM;
+  }
+  if ((e = cudaFuncSetAttribute(k_extract_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ring_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(rings)"); }
+  const size_t scatter_smem = sizeof(uint32_t) * (INGEST_THREADS / 32) * h->opt.max_rings;
+  if (scatter_smem > 48 * 1024) {
+    if ((e = cudaFuncSetAttribute(k_ring_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter)"); }
+  }
+  int occ = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extract_rings, RING_THREADS, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
+  h->ring_grid = h->num_sms * std::max(occ, 1);
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_copy, 256, 0)) != cudaSuccess) { return bail(e, "occupancy(pack)"); }
+  h->pack_grid = h->num_sms * std::max(occ, 1);
+
+  if ((e = cudaMalloc(reinterpret_cast<void **>(&h->d_counters), sizeof(uint32_t) * C_COUNT)) != cudaSuccess) { return bail(e, "cudaMalloc(counters)"); }
+  if ((e = cudaMallocHost(reinterpret_cast<void **>(&h->h_counters), sizeof(uint32_t) * C_COUNT)) != cudaSuccess) { return bail(e, "cudaMallocHost(counters)"); }
+  for (auto & ev : h->ev) {
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) { return bail(e, "cudaEventCreate"); }
+  }
+  *out = h;
+  return LFX_OK;
+}
+
+void lfx_destroy(lfx_handle * h)
+{
+  if (!h) { return; }
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); }
+  drop_graphs(h);
+  cudaFree(h->d_scans.p); cudaFree(h->d_point_base.p); cudaFree(h->d_ring16.p); cudaFree(h->d_tile_hist.p);
+  cudaFree(h->d_rings.p); cudaFree(h->d_work.p); cudaFree(h->d_ring_featoff.p); cudaFree(h->d_idx.p);
+  cudaFree(h->d_labels.p); cudaFree(h->d_sorted_src.p); cudaFree(h->d_curv.p); cudaFree(h->d_stage.p);
+  cudaFree(h->d_edge.p); cudaFree(h->d_surface.p); cudaFree(h->d_counts.p); cudaFree(h->d_offsets.p);
+  cudaFree(h->d_input.p); cudaFree(h->d_counters);
+  cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
+  cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
+  for (auto & ev : h->ev) { if (ev) { cudaEventDestroy(ev); } }
+  if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); }
+  delete h;
+}
+
+int lfx_get_params(const lfx_handle * h, lfx_params * out)
+{
+  if (!h || !out) { return LFX_E_BAD_PARAM; }
+  *out = h->params;
+  return LFX_OK;
+}
+
+int lfx_device(const lfx_handle * h) { return h ? h->device : -1; }
+
+int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans, lfx_batch_result * out)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (n_scans < 0 || (n_scans > 0 && !scans)) { return fail(h, LFX_E_BAD_PARAM, "bad scans argument"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  h->have_batch = false;
+  h->have_timing = false;
+
+  // ---- validate (feature_extraction.cpp:96-108) and lay the batch out
+  uint64_t total_points = 0, total_tiles = 0;
+  size_t input_bytes = 0;
+  for (int s = 0; s < n_scans; s++) {
+    const lfx_cloud_view & v = scans[s];
+    if (!v.is_dense) { return fail(h, LFX_E_NOT_DENSE, "Point cloud is not in dense format, please remove NaN points first!"); }
+    if (!v.has_ring) { return fail(h, LFX_E_NO_RING, "Ring channel could not be found"); }
+    if (v.ring_datatype != LFX_RING_U8 && v.ring_datatype != LFX_RING_U16 && v.ring_datatype != LFX_RING_U32) {
+      return fail(h, LFX_E_BAD_LAYOUT, "ring field must be UINT8, UINT16 or UINT32");
+    }
+    const uint32_t ring_bytes = v.ring_datatype == LFX_RING_U8 ? 1 : (v.ring_datatype == LFX_RING_U16 ? 2 : 4);
+    if (v.n_points > 0 && !v.data) { return fail(h, LFX_E_BAD_LAYOUT, "null data with n_points > 0"); }
+    if (v.point_step < 12 || v.off_x + 4 > v.point_step || v.off_y + 4 > v.point_step || v.off_z + 4 > v.point_step ||
+        v.off_ring + ring_bytes > v.point_step) {
+      return fail(h, LFX_E_BAD_LAYOUT, "field offsets exceed point_step");
+    }
+    if ((v.point_step | v.off_x | v.off_y | v.off_z) % 4 != 0 || v.off_ring % ring_bytes != 0 ||
+        (v.memory == LFX_MEM_DEVICE && reinterpret_cast<uintptr_t>(v.data) % 4 != 0)) {
+      return fail(h, LFX_E_BAD_LAYOUT, "x/y/z must be 4-byte aligned and ring naturally aligned");
+    }
+    total_points += v.n_points;
+    total_tiles += (v.n_points + TILE - 1) / TILE;
+    if (v.memory == LFX_MEM_HOST) { input_bytes += ((size_t)v.n_points * v.point_step + 15) & ~(size_t)15; }
+  }
+  if (total_points >= 0xFFFF0000ull) { return fail(h, LFX_E_CAPACITY, "batch exceeds 2^32 points"); }
+
+  // ---- capacity
+  const size_t np = std::max<uint64_t>(total_points, 1), ns = std::max(n_scans, 1);
+  const size_t mr = h->opt.max_rings;
+  bool regrown = false;
+  int rc;
+  if ((rc = ensure(h, h->d_scans, ns, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_point_base, ns + 1, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_ring16, np, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_tile_hist, std::max<uint64_t>(total_tiles, 1) * mr, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_rings, ns * mr, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_work, ns * mr, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_ring_featoff, ns * mr, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_idx, np, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_labels, np, &regrown))) { return rc; }
+  if (h->opt.want_sorted_src && (rc = ensure(h, h->d_sorted_src, np, &regrown))) { return rc; }
+  if (h->opt.want_curvature && (rc = ensure(h, h->d_curv, np, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_stage, np, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_edge, np, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_surface, np, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_counts, ns * 2, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_offsets, (ns + 1) * 2, &regrown))) { return rc; }
+  if (input_bytes && (rc = ensure(h, h->d_input, input_bytes, &regrown))) { return rc; }
+  if (regrown) { drop_graphs(h); }
+  if (ns + 1 > h->h_scans_cap) {
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base);
+    h->h_scans = nullptr; h->h_point_base = nullptr;
+    const size_t want = ns + ns / 8 + 8;
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_scans), want * sizeof(ScanDesc)));
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_point_base), (want + 1) * sizeof(uint64_t)));
+    h->h_scans_cap = want;
+  } else {
+    // the pinned descriptor table of the previous batch may still be in flight
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+
+  // ---- descriptors + H2D of host-resident payloads (adjacent host buffers coalesce into one copy)
+  uint64_t pb = 0;
+  uint32_t tb = 0;
+  size_t in_off = 0;
+  const uint8_t * run_src = nullptr;
+  size_t run_dst = 0, run_len = 0;
+  auto flush = [&]() -> cudaError_t {
+    if (!run_len) { return cudaSuccess; }
+    cudaError_t e = cudaMemcpyAsync(h->d_input.p + run_dst, run_src, run_len, cudaMemcpyHostToDevice, h->stream);
+    run_len = 0;
+    return e;
+  };
+  for (int s = 0; s < n_scans; s++) {
+    const lfx_cloud_view & v = scans[s];
+    ScanDesc & d = h->h_scans[s];
+    const size_t bytes = (size_t)v.n_points * v.point_step;
+    if (v.memory == LFX_MEM_HOST) {
+      d.data = h->d_input.p + in_off;
+      if (bytes) {
+        const uint8_t * src = static_cast<const uint8_t *>(v.data);
+        if (run_len && run_src + run_len == src && run_dst + run_len == in_off) { run_len += bytes; }
+        else { LFX_CUDA(h, flush()); run_src = src; run_dst = in_off; run_len = bytes; }
+      }
+      in_off += (bytes + 15) & ~(size_t)15;
+    } else {
+      d.data = static_cast<const uint8_t *>(v.data);
+    }
+    d.point_base = pb;
+    d.n_points = v.n_points;
+    d.point_step = v.point_step;
+    d.off_x = v.off_x; d.off_y = v.off_y; d.off_z = v.off_z; d.off_ring = v.off_ring;
+    d.ring_dt = v.ring_datatype;
+    d.tile_base = tb;
+    d.n_tiles = (v.n_points + TILE - 1) / TILE;
+    d.vec_ok = (v.off_y == v.off_x + 4 && v.off_z == v.off_x + 8 && v.off_x % 16 == 0 && v.point_step % 16 == 0 &&
+                v.off_x + 16 <= v.point_step && reinterpret_cast<uintptr_t>(d.data) % 16 == 0) ? 1u : 0u;
+    h->h_point_base[s] = pb;
+    pb += v.n_points;
+    tb += d.n_tiles;
+  }
+  LFX_CUDA(h, flush());
+  h->h_point_base[n_scans] = pb;
+  if (n_scans > 0) {
+    LFX_CUDA(h, cudaMemcpyAsync(h->d_scans.p, h->h_scans, sizeof(ScanDesc) * n_scans, cudaMemcpyHostToDevice, h->stream));
+  }
+  LFX_CUDA(h, cudaMemcpyAsync(h->d_point_base.p, h->h_point_base, sizeof(uint64_t) * (n_scans + 1), cudaMemcpyHostToDevice, h->stream));
+
+  // ---- launch
+  h->n_scans = n_scans;
+  h->total_points = total_points;
+  h->total_tiles = (uint32_t)total_tiles;
+  if (n_scans > 0) {
+    const bool use_graph = h->opt.use_graph >= 0 && !h->timing;
+    if (use_graph) {
+      const GraphKey key{n_scans, (uint32_t)total_tiles};
+      auto it = h->graphs.find(key);
+      if (it == h->graphs.end()) {
+        cudaGraph_t g = nullptr;
+        LFX_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, false);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (rc) { if (g) { cudaGraphDestroy(g); } return rc; }
+        if (e != cudaSuccess) { return fail(h, LFX_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); }
+        cudaGraphExec_t ge = nullptr;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { return fail(h, LFX_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        if (h->graphs.size() >= 64) { drop_graphs(h); }
+        it = h->graphs.emplace(key, ge).first;
+      }
+      LFX_CUDA(h, cudaGraphLaunch(it->second, h->stream));
+    } else {
+      if ((rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, h->timing))) { return rc; }
+      h->have_timing = h->timing;
+    }
+    h->launches += KERNELS_PER_BATCH - (total_tiles == 0 ? 2 : 0);
+  } else {
+    LFX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * C_COUNT, h->stream));
+    LFX_CUDA(h, cudaMemsetAsync(h->d_offsets.p, 0, sizeof(uint32_t) * 2, h->stream));
+  }
+  h->have_batch = true;
+
+  if (out) {
+    out->n_scans = n_scans;
+    out->total_points = total_points;
+    out->d_edge_xyz = reinterpret_cast<const float *>(h->d_edge.p);
+    out->d_surface_xyz = reinterpret_cast<const float *>(h->d_surface.p);
+    out->d_counts = h->d_counts.p;
+    out->d_offsets = h->d_offsets.p;
+    out->d_labels = h->d_labels.p;
+    out->d_sorted_src = h->opt.want_sorted_src ? h->d_sorted_src.p : nullptr;
+    out->d_curvature = h->opt.want_curvature ? h->d_curv.p : nullptr;
+    out->d_rings = h->d_rings.p;
+    out->d_point_base = h->d_point_base.p;
+    out->max_rings = h->opt.max_rings;
+  }
+  return LFX_OK;
+}
+
+int lfx_synchronize(lfx_handle * h)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_batch_status(lfx_handle * h)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(uint32_t) * C_COUNT, cudaMemcpyDeviceToHost, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->h_counters[C_ERR_FLAG]) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "capacity exceeded at scan %u, ring %u (raise lfx_options.max_ring_points / max_rings)",
+             h->h_counters[C_ERR_SCAN], h->h_counters[C_ERR_RING]);
+    return fail(h, (int)h->h_counters[C_ERR_FLAG], buf);
+  }
+  return LFX_OK;
+}
+
+int lfx_fetch_counts(lfx_handle * h, uint32_t * counts, uint32_t * offsets)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  if (counts && h->n_scans) { LFX_CUDA(h, cudaMemcpyAsync(counts, h->d_counts.p, sizeof(uint32_t) * 2 * h->n_scans, cudaMemcpyDeviceToHost, h->stream)); }
+  if (offsets) { LFX_CUDA(h, cudaMemcpyAsync(offsets, h->d_offsets.p, sizeof(uint32_t) * 2 * (h->n_scans + 1), cudaMemcpyDeviceToHost, h->stream)); }
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_fetch_features(lfx_handle * h, float * edge_xyz, size_t edge_capacity_points, float * surface_xyz,
+                       size_t surface_capacity_points)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  uint32_t tot[2];
+  LFX_CUDA(h, cudaMemcpyAsync(tot, h->d_offsets.p + 2 * h->n_scans, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if ((edge_xyz && tot[0] > edge_capacity_points) || (surface_xyz && tot[1] > surface_capacity_points)) {
+    return fail(h, LFX_E_CAPACITY, "feature output buffer too small");
+  }
+  if (edge_xyz && tot[0]) { LFX_CUDA(h, cudaMemcpyAsync(edge_xyz, h->d_edge.p, sizeof(float4) * tot[0], cudaMemcpyDeviceToHost, h->stream)); }
+  if (surface_xyz && tot[1]) { LFX_CUDA(h, cudaMemcpyAsync(surface_xyz, h->d_surface.p, sizeof(float4) * tot[1], cudaMemcpyDeviceToHost, h->stream)); }
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_fetch_points(lfx_handle * h, uint8_t * labels, uint32_t * sorted_src, double * curvature)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  if (sorted_src && !h->opt.want_sorted_src) { return fail(h, LFX_E_STATE, "handle was created without want_sorted_src"); }
+  if (curvature && !h->opt.want_curvature) { return fail(h, LFX_E_STATE, "handle was created without want_curvature"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  const size_t n = h->total_points;
+  if (n) {
+    if (labels) { LFX_CUDA(h, cudaMemcpyAsync(labels, h->d_labels.p, n, cudaMemcpyDeviceToHost, h->stream)); }
+    if (sorted_src) { LFX_CUDA(h, cudaMemcpyAsync(sorted_src, h->d_sorted_src.p, n * 4, cudaMemcpyDeviceToHost, h->stream)); }
+    if (curvature) { LFX_CUDA(h, cudaMemcpyAsync(curvature, h->d_curv.p, n * 8, cudaMemcpyDeviceToHost, h->stream)); }
+  }
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_fetch_rings(lfx_handle * h, lfx_ring_info * rings)
+{
+  if (!h || !rings) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  if (h->n_scans) {
+    LFX_CUDA(h, cudaMemcpyAsync(rings, h->d_rings.p, sizeof(lfx_ring_info) * (size_t)h->n_scans * h->opt.max_rings, cudaMemcpyDeviceToHost, h->stream));
+  }
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_extract_scan(lfx_handle * h, const lfx_cloud_view * scan, lfx_scan_output * out)
+{
+  if (!h || !scan || !out) { return LFX_E_BAD_PARAM; }
+  int rc = lfx_extract_batch(h, scan, 1, nullptr);
+  if (rc) { return rc; }
+  const size_t n = std::max<size_t>(scan->n_points, 1);
+  if (n > h->h_scan_cap) {
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
+    h->h_edge = h->h_surface = nullptr; h->h_labels = nullptr; h->h_sorted_src = nullptr; h->h_scan_cap = 0;
+    const size_t want = n + n / 8;
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_edge), want * sizeof(float4)));
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_surface), want * sizeof(float4)));
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_labels), want));
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_sorted_src), want * sizeof(uint32_t)));
+    h->h_scan_cap = want;
+  }
+  uint32_t counts[2] = {0, 0};
+  if ((rc = lfx_fetch_counts(h, counts, nullptr))) { return rc; }
+  if ((rc = lfx_fetch_features(h, reinterpret_cast<float *>(h->h_edge), h->h_scan_cap, reinterpret_cast<float *>(h->h_surface), h->h_scan_cap))) { return rc; }
+  if ((rc = lfx_fetch_points(h, h->h_labels, h->opt.want_sorted_src ? h->h_sorted_src : nullptr, nullptr))) { return rc; }
+  if ((rc = lfx_batch_status(h))) { return rc; }
+  out->edge_xyz = reinterpret_cast<const float *>(h->h_edge);
+  out->surface_xyz = reinterpret_cast<const float *>(h->h_surface);
+  out->n_edge = counts[0];
+  out->n_surface = counts[1];
+  out->labels = h->h_labels;
+  out->sorted_src = h->opt.want_sorted_src ? h->h_sorted_src : nullptr;
+  out->n_points = scan->n_points;
+  return LFX_OK;
+}
+
+int lfx_label_to_color(uint8_t label, uint8_t * rgb)
+{
+  // LabelToColor, extraction/src/color_points.cpp:39-68
+  static const uint8_t table[8][3] = {{255, 255, 255}, {255, 0, 0}, {255, 63, 0}, {255, 0, 0},
+                                      {255, 63, 0}, {127, 127, 127}, {255, 0, 255}, {0, 255, 0}};
+  if (label > 7 || !rgb) { return LFX_E_BAD_PARAM; }  // ThrowIfInvalidLabelDetected color_points.cpp:33-37
+  memcpy(rgb, table[label], 3);
+  return LFX_OK;
+}
+
+// ---------------------------------------------------------------- memory helpers
+
+void * lfx_host_alloc(size_t bytes)
+{
+  void * p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { return nullptr; }
+  return p;
+}
+
+void lfx_host_free(void * p) { if (p) { cudaFreeHost(p); } }
+
+int lfx_device_alloc(lfx_handle * h, size_t bytes, void ** out)
+{
+  if (!h || !out) { return LFX_E_BAD_PARAM; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMalloc(out, bytes ? bytes : 1));
+  return LFX_OK;
+}
+
+int lfx_device_free(lfx_handle * h, void * p)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  LFX_CUDA(h, cudaFree(p));
+  return LFX_OK;
+}
+
+int lfx_memcpy_h2d(lfx_handle * h, void * dst, const void * src, size_t bytes)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_memcpy_d2h(lfx_handle * h, void * dst, const void * src, size_t bytes)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+// ---------------------------------------------------------------- instrumentation
+
+uint64_t lfx_kernel_launch_count(const lfx_handle * h) { return h ? h->launches : 0; }
+
+int lfx_set_stage_timing(lfx_handle * h, int enabled)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  h->timing = enabled != 0;
+  return LFX_OK;
+}
+
+int lfx_last_stage_ms(lfx_handle * h, float * ms3)
+{
+  if (!h || !ms3) { return LFX_E_BAD_PARAM; }
+  if (!h->have_timing) { return fail(h, LFX_E_STATE, "stage timing was not enabled for the last batch"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaEventSynchronize(h->ev[3]));
+  for (int k = 0; k < 3; k++) { LFX_CUDA(h, cudaEventElapsedTime(&ms3[k], h->ev[k], h->ev[k + 1])); }
+  return LFX_OK;
+}
+
+// ---------------------------------------------------------------- synthetic scans
+
+int lfx_synth_named(const char * name, lfx_synth_spec * out)
+{
+  if (!name || !out) { return LFX_E_BAD_PARAM; }
+  lfx_synth_spec s{};
+  s.range_noise = 0.005f;
+  s.dropout_prob = 0.0f;
+  s.dropout_burst = 16.0f;
+  s.near_prob = 0.0f;
+  s.world = LFX_WORLD_ROOM;
+  const std::string n(name);
+  if (n == "vlp16") { s.n_rings = 16; s.n_cols = 1800; s.elev_lo_deg = -15.0f; s.elev_hi_deg = 15.0f; s.seed = 0xC0FFEEull ^ 1; }
+  else if (n == "hdl32") { s.n_rings = 32; s.n_cols = 2170; s.elev_lo_deg = -30.67f; s.elev_hi_deg = 10.67f; s.seed = 0xC0FFEEull ^ 2; }
+  else if (n == "hdl64") {
+    s.n_rings = 64; s.n_cols = 2048; s.elev_lo_deg = 2.0f; s.elev_hi_deg = -24.8f; s.seed = 0xC0FFEEull ^ 3;
+    s.world = LFX_WORLD_TUNNEL; s.dropout_prob = 0.01f; s.near_prob = 0.0005f;
+  }
+  else if (n == "os128") { s.n_rings = 128; s.n_cols = 2048; s.elev_lo_deg = -22.5f; s.elev_hi_deg = 22.5f; s.seed = 0xC0FFEEull ^ 4; }
+  else { return LFX_E_BAD_PARAM; }
+  *out = s;
+  return LFX_OK;
+}
+
+int lfx_synth_scan_host(const lfx_synth_spec * spec, uint64_t frame, void * out, uint32_t * n_points_out)
+{
+  if (!spec || !out || !n_points_out || spec->n_rings <= 0 || spec->n_cols <= 0 || spec->n_rings > 65535) { return LFX_E_BAD_PARAM; }
+  lfx_synth::Point32 * p = static_cast<lfx_synth::Point32 *>(out);
+  const float az0 = lfx_synth::start_azimuth(*spec, frame);
+  uint32_t n = 0;
+  for (int col = 0; col < spec->n_cols; col++) {
+    for (int ring = 0; ring < spec->n_rings; ring++) {
+      if (lfx_synth::make_point(*spec, frame, az0, (uint32_t)ring, (uint32_t)col, &p[n])) { n++; }
+    }
+  }
+  *n_points_out = n;
+  return LFX_OK;
+}
+
+}  // extern "C"
+
+namespace
+{
+__global__ void k_synth(const lfx_synth_spec spec, uint64_t first_frame, int n_scans, lfx_synth::Point32 * out)
+{
+  const size_t per_scan = (size_t)spec.n_rings * spec.n_cols;
+  const size_t total = per_scan * n_scans;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const uint64_t scan = g / per_scan;
+    const uint32_t k = (uint32_t)(g - scan * per_scan);
+    const uint32_t col = k / spec.n_rings, ring = k - col * spec.n_rings;
+    const uint64_t frame = first_frame + scan;
+    const float az0 = lfx_synth::start_azimuth(spec, frame);
+    lfx_synth::Point32 p;
+    lfx_synth_spec s2 = spec;
+    s2.dropout_prob = 0.0f;
+    lfx_synth::make_point(s2, frame, az0, ring, col, &p);
+    out[g] = p;
+  }
+}
+}  // namespace
+
+extern "C" int lfx_synth_batch_device(lfx_handle * h, const lfx_synth_spec * spec, uint64_t first_frame, int n_scans, void * d_out)
+{
+  if (!h || !spec || !d_out || n_scans < 0 || spec->n_rings <= 0 || spec->n_cols <= 0) { return LFX_E_BAD_PARAM; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  if (n_scans == 0) { return LFX_OK; }
+  k_synth<<<h->num_sms * 8, 256, 0, h->stream>>>(*spec, first_frame, n_scans, static_cast<lfx_synth::Point32 *>(d_out));
+  LFX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  return LFX_OK;
+}
