@@ -1,0 +1,96 @@
+"""Host-side checks that run without a GPU: the C-ABI library loads, exports every symbol the header
+declares, mirrors the reference's parameter sets, and FAILS LOUDLY without a device (no CPU fallback)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from lidar_feature_extraction_b200 import _native as N
+
+
+def test_library_exports_every_declared_symbol():
+    lib = N.lib()
+    names = N.declared_symbols()
+    assert len(names) >= 28
+    missing = [s for s in names if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_parameter_sets_match_reference():
+    from lidar_feature_extraction_b200 import default_params, launch_yaml_params
+
+    d = default_params()   # hyper_parameter.hpp:35-43
+    assert (d.padding, d.neighbor_degree_threshold, d.distance_diff_threshold, d.parallel_beam_min_range_ratio,
+            d.edge_threshold, d.surface_threshold, d.min_range, d.max_range, d.n_blocks) == (5, 2.0, 0.3, 0.02, 0.05, 0.05, 0.1, 100.0, 6)
+    y = launch_yaml_params()  # lidar_feature_extraction.param.yaml:3-10
+    assert (y.padding, y.neighbor_degree_threshold, y.distance_diff_threshold, y.parallel_beam_min_range_ratio,
+            y.edge_threshold, y.surface_threshold, y.min_range, y.max_range, y.n_blocks) == (2, 3.0, 0.3, 0.02, 50.0, 0.05, 0.1, 1000.0, 6)
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(N.Params) == 72
+    assert C.sizeof(N.CloudView) == 40
+    assert C.sizeof(N.RingInfo) == 24
+    assert C.sizeof(N.SynthSpec) == 48
+
+
+def test_label_to_color_matches_reference_table():
+    from lidar_feature_extraction_b200 import label_to_color
+
+    # color_points.cpp:39-68
+    assert [label_to_color(k) for k in range(8)] == [(255, 255, 255), (255, 0, 0), (255, 63, 0), (255, 0, 0), (255, 63, 0),
+                                                     (127, 127, 127), (255, 0, 255), (0, 255, 0)]
+    with pytest.raises(ValueError):
+        label_to_color(8)
+
+
+def test_invalid_parameters_are_rejected_before_touching_cuda():
+    lib = N.lib()
+    for field in ("padding", "n_blocks", "edge_threshold", "min_range"):
+        p = N.Params()
+        lib.lfx_default_params(C.byref(p))
+        setattr(p, field, 0)
+        h = C.c_void_p()
+        assert lib.lfx_create(C.byref(p), None, C.byref(h)) == N.LFX_E_BAD_PARAM  # hyper_parameter.hpp:45-53
+        assert b"> 0" in lib.lfx_last_error(None)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from lidar_feature_extraction_b200 import ExtractionError, FeatureExtraction
+
+    with pytest.raises(ExtractionError) as e:
+        FeatureExtraction()
+    assert e.value.code == N.LFX_E_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "lidar_feature_extraction_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "lfx_oracle" not in text and "from oracle" not in text and "import oracle" not in text, f
+
+
+def test_synthetic_generator_shapes_and_determinism():
+    from lidar_feature_extraction_b200 import synth
+
+    for name, (r, w) in {"vlp16": (16, 1800), "hdl32": (32, 2170), "os128": (128, 2048)}.items():
+        sp = synth.spec(name)
+        a, b = synth.scan_host(sp, 7), synth.scan_host(sp, 7)
+        assert a.shape == (r * w, 32) and np.array_equal(a, b)
+        x, y, z, _, ring = synth.fields(a)
+        assert np.array_equal(ring.reshape(w, r)[0], np.arange(r))  # column-major firing order
+        assert not ((x == 0) & (y == 0) & (z == 0)).any()            # convert.py drops (0,0,0) upstream
+        az = np.arctan2(y, x).reshape(w, r)
+        for k in (0, r - 1):                                         # strictly distinct azimuths per ring
+            assert len(np.unique(az[:, k])) == w
+    hd = synth.scan_host(synth.spec("hdl64"), 0)
+    assert 0 < len(hd) < 64 * 2048                                   # drop-outs make it ragged
