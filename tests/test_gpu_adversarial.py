@@ -125,7 +125,7 @@ def test_sparse_ring_ids_and_general_layouts(oracle):
     from oracle import binding as ob
 
     base = adv.ragged_scan(5, [150, 90, 400], ring_ids=[3, 77, 100], shuffle="interleave")
-    x, y, z, _, ring = synth.fields(base)
+    x, y, z, _, ring = (np.ascontiguousarray(a) for a in synth.fields(base))
     hp = _hp()
     want = oracle.extract_scan(base, oracle_params(ob, hp))
     for step, ox, oy, oz, oring, rdt, npdt in ((48, 16, 4, 32, 44, 6, np.uint32), (20, 0, 4, 8, 13, 2, np.uint8), (32, 12, 8, 4, 0, 4, np.uint16)):
