@@ -19,6 +19,7 @@
 
 #include "lfx.h"
 #include "lfx_kernels.cuh"
+#include "lfx_ring.cuh"
 #include "lfx_synth.h"
 
 using namespace lfxk;
@@ -53,7 +54,9 @@ struct lfx_handle
   int num_sms = 0;
   int ring_grid = 0, pack_grid = 0;
   size_t ring_smem = 0;
-  int cap = 0, cap2 = 0;
+  int cap = 0;
+  int ring_threads = 0;
+  void (*ring_kernel)(const RingArgs) = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -154,7 +157,37 @@ double cos_cut(double theta)
   return unkey(hi);
 }
 
-int next_pow2(int v) { int p = 32; while (p < v) { p <<= 1; } return p; }
+// Smallest double q with (double)(float)q > rho: the parallel-beam test of parallel_beam.hpp:44-47
+// narrows the ratio to float before comparing, so the predicate is monotone in q and has a single cut.
+double ratio_cut(double rho)
+{
+  auto key = [](double v) { int64_t b; memcpy(&b, &v, 8); return b; };          // q >= 0 only
+  auto unkey = [](int64_t k) { double v; memcpy(&v, &k, 8); return v; };
+  auto pred = [&](double q) { const float f = (float)q; return (double)f > rho; };
+  int64_t lo = key(0.0), hi = key(1.7976931348623157e308);  // pred(lo) false (rho > 0), pred(hi) true ((float)DBL_MAX = inf)
+  if (!pred(unkey(hi))) { return INFINITY; }
+  while (hi - lo > 1) {
+    const int64_t mid = lo + (hi - lo) / 2;
+    if (pred(unkey(mid))) { hi = mid; } else { lo = mid; }
+  }
+  return unkey(hi);
+}
+
+template<int PT>
+void (*pick_ring_kernel_t(int threads, int * tmax))(const RingArgs)
+{
+  if (threads <= 288) { *tmax = 288; return k_extract_rings2<PT, 288, 3>; }
+  if (threads <= 512) { *tmax = 512; return k_extract_rings2<PT, 512, 1>; }
+  *tmax = 1024;
+  return k_extract_rings2<PT, 1024, 1>;
+}
+
+void (*pick_ring_kernel(int padding, int threads, int * tmax))(const RingArgs)
+{
+  if (padding == 5) { return pick_ring_kernel_t<5>(threads, tmax); }   // compiled default
+  if (padding == 2) { return pick_ring_kernel_t<2>(threads, tmax); }   // launch YAML
+  return pick_ring_kernel_t<0>(threads, tmax);                         // any other padding: runtime loops
+}
 
 int validate_params(const lfx_params & p, std::string & why)
 {
@@ -199,10 +232,9 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   ra.stage = h->d_stage.p;
   ra.max_rings = max_rings;
   ra.cap = h->cap;
-  ra.cap2 = h->cap2;
   ra.force_order_path = h->opt.force_order_path;
   ra.prm = h->dev;
-  k_extract_rings<<<h->ring_grid, RING_THREADS, h->ring_smem, h->stream>>>(ra);
+  h->ring_kernel<<<h->ring_grid, h->ring_threads, h->ring_smem, h->stream>>>(ra);
   if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
   k_feat_offsets_a<<<n_scans, 128, 0, h->stream>>>(h->d_rings.p, h->d_ring_featoff.p, h->d_counts.p, max_rings);
   k_feat_offsets_b<<<1, 1024, 0, h->stream>>>(h->d_counts.p, h->d_offsets.p, n_scans);
@@ -270,8 +302,8 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
     return LFX_E_BAD_PARAM;
   }
   h->device = h->opt.device;
-  h->cap = (std::max(h->opt.max_ring_points, 2 * params->padding + 2) + 63) & ~63;
-  h->cap2 = next_pow2(h->cap);
+  h->cap = (std::max(h->opt.max_ring_points, 2 * params->padding + 2) + 255) & ~255;
+  h->ring_threads = h->cap / PTS;
 
   auto bail = [&](cudaError_t e, const char * what) {
     g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -299,6 +331,11 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->dev.P = params->padding;
   h->dev.B = params->n_blocks;
   h->dev.c_min = cos_cut(params->neighbor_degree_threshold * M_PI / 180.0);  // DegreeToRadian degree_to_radian.hpp:34-37
+  h->dev.c_lo = h->dev.c_min * (1.0 - 0x1p-40);
+  h->dev.c_hi = h->dev.c_min * (1.0 + 0x1p-40);
+  h->dev.q_min = ratio_cut(params->parallel_beam_min_range_ratio);
+  h->dev.q_lo = h->dev.q_min * (1.0 - 0x1p-40);
+  h->dev.q_hi = h->dev.q_min * (1.0 + 0x1p-40);
   h->dev.d = params->distance_diff_threshold;
   h->dev.rho = params->parallel_beam_min_range_ratio;
   h->dev.tau_e = params->edge_threshold;
@@ -308,19 +345,21 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->dev.center_w = -2. * params->padding;  // MakeWeight curvature.cpp:40
 
   // kernel attributes / persistent grid sizes
-  h->ring_smem = ring_smem_bytes(h->cap, h->cap2);
+  h->ring_smem = ring2_smem_bytes(h->cap, params->padding);
   if (h->ring_smem > (size_t)prop.sharedMemPerBlockOptin) {
     g_create_error = "max_ring_points does not fit in shared memory";
     lfx_destroy(h);
     return LFX_E_BAD_PARAM;
   }
-  if ((e = cudaFuncSetAttribute(k_extract_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ring_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(rings)"); }
+  int tmax = 0;
+  h->ring_kernel = pick_ring_kernel(params->padding, h->ring_threads, &tmax);
+  if ((e = cudaFuncSetAttribute(h->ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ring_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(rings)"); }
   const size_t scatter_smem = sizeof(uint32_t) * (INGEST_THREADS / 32) * h->opt.max_rings;
   if (scatter_smem > 48 * 1024) {
     if ((e = cudaFuncSetAttribute(k_ring_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter)"); }
   }
   int occ = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extract_rings, RING_THREADS, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->ring_kernel, h->ring_threads, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
   h->ring_grid = h->num_sms * std::max(occ, 1);
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_copy, 256, 0)) != cudaSuccess) { return bail(e, "occupancy(pack)"); }
   h->pack_grid = h->num_sms * std::max(occ, 1);

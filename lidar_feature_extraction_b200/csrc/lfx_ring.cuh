@@ -1,0 +1,647 @@
+// lfx_ring.cuh — the per-ring kernel (v2): everything in feature_extraction.cpp:121-151 for one ring,
+// held in shared memory by one CTA.
+//
+// Shape of the computation (why it looks the way it does):
+//  * the kernel is instruction-issue bound, not DRAM bound (profiles/r01a): so every thread owns EIGHT
+//    consecutive ring positions, keeps the XY-range / curvature sliding windows in registers, and writes
+//    each per-point predicate as one BYTE of a bit stream (no ballots, no per-point smem round trips);
+//  * everything that is a neighbourhood predicate (conflict windows, greedy selection, cover fills,
+//    occlusion fills, label priority) then runs bit-sliced on 32-point words: one thread per word,
+//    ~1 instruction per point per sweep.
+//  * all roundings that decide a label are IEEE-exact and uncontracted; divisions are replaced by
+//    guard-banded multiplications with an exact fallback inside the band.
+#ifndef LFX_RING_CUH_
+#define LFX_RING_CUH_
+
+#include "lfx_kernels.cuh"
+
+namespace lfxk
+{
+
+constexpr int PTS = 8;  // consecutive ring positions per thread
+
+// bit-stream arrays (one bit per ring position)
+enum BitArray {
+  A_LINK = 0,  // is_neighbor(i, i+1)                                   neighbor.hpp:44-48
+  A_LS,        // link usable by the selection: both ends inside one sector  label.hpp:153-163
+  A_TL,        // left occlusion trigger at k = i                        occlusion.hpp:45-53
+  A_TRS,       // right occlusion trigger at k = i + 1                   occlusion.hpp:67-75
+  A_OOR,       // out of range                                           out_of_range.hpp:36-48
+  A_PB,        // parallel beam                                          parallel_beam.hpp:36-51
+  A_E,         // edge candidate: inside && curvature >= edge_threshold  label.hpp:81-83
+  A_S0,        // surface candidate before the edge pass: inside && curvature <= surface_threshold
+  A_SB,        // i is the last position of a sector (or outside [P, n-P-1))
+  A_XE,        // picked Edge
+  A_XS,        // picked Surface
+  A_L0, A_L1, A_L2,  // bit planes of the final label
+  A_EM, A_SM,  // final label == Edge / == Surface
+  A_C0,        // A_C0 + d - 1: curvature(i + d) >= curvature(i), d = 1..P   (key order, ties by index)
+  A_COUNT_FIXED = A_C0
+};
+
+struct RingSmem2
+{
+  float * fx, * fy, * fz;   // bucket-order coordinates, padded: slot(q) = q + (q >> 5)
+  double * dr;              // XY range by sorted position, padded: slot(p) = p + (p >> 4), halo of 32 each side
+  uint32_t * bits;          // [n_arrays][nwords] ; word 0 of each array is a zero pad
+  uint32_t * wpre;          // [2][nwords] exclusive prefix of per-word Edge / Surface counts
+  uint16_t * perm;          // [cap] sorted position -> bucket position (sort path only)
+  int * bnd;                // [MAX_BLOCKS + 1]
+  int * misc;               // [16]
+  int nwords;               // words per bit array = cap / 32 + 4
+};
+
+__host__ __device__ inline int ring2_arrays(int P) { return A_COUNT_FIXED + P; }
+
+__host__ __device__ inline size_t ring2_smem_bytes(int cap, int P)
+{
+  const int nwords = cap / 32 + 4;
+  size_t b = 0;
+  b += (size_t)(cap + cap / 32 + 8) * 4 * 3;        // fx, fy, fz
+  b += (size_t)(cap + cap / 16 + 128) * 8;          // dr (+ halo)
+  b += (size_t)ring2_arrays(P) * nwords * 4;        // bit streams
+  b += (size_t)2 * nwords * 4;                      // wpre
+  b += (size_t)cap * 2;                             // perm
+  b += (MAX_BLOCKS + 1) * 4 + 16 * 4;
+  return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ RingSmem2 carve2(unsigned char * base, int cap, int P)
+{
+  RingSmem2 s;
+  s.nwords = cap / 32 + 4;
+  const size_t fl = (size_t)(cap + cap / 32 + 8);
+  s.dr = reinterpret_cast<double *>(base) + 32; base += (size_t)(cap + cap / 16 + 128) * 8;
+  s.fx = reinterpret_cast<float *>(base); base += fl * 4;
+  s.fy = reinterpret_cast<float *>(base); base += fl * 4;
+  s.fz = reinterpret_cast<float *>(base); base += fl * 4;
+  s.bits = reinterpret_cast<uint32_t *>(base); base += (size_t)ring2_arrays(P) * s.nwords * 4;
+  s.wpre = reinterpret_cast<uint32_t *>(base); base += (size_t)2 * s.nwords * 4;
+  s.bnd = reinterpret_cast<int *>(base); base += (MAX_BLOCKS + 1) * 4;
+  s.misc = reinterpret_cast<int *>(base); base += 16 * 4;
+  s.perm = reinterpret_cast<uint16_t *>(base);
+  return s;
+}
+
+enum Misc2 { N_WORK = 0, N_CNT_ASC = 1, N_POS_NONASC = 2, N_POS_ASC = 3, N_SKIP = 4 };
+
+__device__ __forceinline__ int fslot(int q) { return q + (q >> 5); }
+__device__ __forceinline__ int dslot(int p) { return p + (p >> 4); }
+
+// word helpers on a bit stream X (pointer to its word 0 = front pad): data word w is X[1 + w]
+__device__ __forceinline__ uint32_t wd(const uint32_t * X, int w) { return X[1 + w]; }
+// bit j of result = X(32 w + j + k), 0 <= k < 32
+__device__ __forceinline__ uint32_t shr_bits(uint32_t cur, uint32_t next, int k) { return __funnelshift_r(cur, next, k); }
+// bit j of result = X(32 w + j - k), 1 <= k < 32
+__device__ __forceinline__ uint32_t shl_bits(uint32_t prev, uint32_t cur, int k) { return __funnelshift_r(prev, cur, 32 - k); }
+
+// spread the 8 bits of b into the low bit of 8 bytes (lo: bits 0-3, hi: bits 4-7)
+__device__ __forceinline__ void spread8(uint32_t b, uint32_t & lo, uint32_t & hi)
+{
+  lo = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
+  hi = (((b >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+
+// 32-bit (19-bit pseudo angle | 13-bit position) sort key for the non-monotone path
+__device__ __forceinline__ uint32_t polar_key19(float x, float y, int q)
+{
+  return (polar_key(x, y) & 0xFFFFE000u) | (uint32_t)q;
+}
+
+__device__ __forceinline__ void bitonic_u32(uint32_t * k, int n2)
+{
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int hi = lo | stride;
+        const bool up = (lo & size) == 0;
+        const uint32_t a = k[lo], b = k[hi];
+        if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// exact fallback: bitonic sort of bucket positions with the reference comparator (padded coordinate arrays)
+__device__ __forceinline__ void bitonic_exact2(uint16_t * p, int n, int n2, const float * fx, const float * fy)
+{
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+        const int hi = lo | stride;
+        const bool up = (lo & size) == 0;
+        const int a = p[lo], b = p[hi];
+        bool a_after_b;
+        if (a >= n || b >= n) { a_after_b = a > b; }
+        else if (polar_less(fx[fslot(b)], fy[fslot(b)], fx[fslot(a)], fy[fslot(a)])) { a_after_b = true; }
+        else if (polar_less(fx[fslot(a)], fy[fslot(a)], fx[fslot(b)], fy[fslot(b)])) { a_after_b = false; }
+        else { a_after_b = a > b; }
+        if (a_after_b == up) { p[lo] = (uint16_t)b; p[hi] = (uint16_t)a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// is_neighbor(i, i+1) for XY points (x0,y0), (x1,y1) with XY ranges r0, r1:
+//   acos(dot / (r0 r1)) < theta   <=>   c_min <= RN(dot / (r0 r1)) <= 1      (host-derived c_min)
+// decided without the division whenever dot is outside a 2^-39-wide guard band around c_min * r0 r1.
+__device__ __forceinline__ bool link_test(double x0, double y0, double x1, double y1, double r0, double r1, const DevParams & prm)
+{
+  const double dot = __dadd_rn(__dmul_rn(x0, x1), __dmul_rn(y0, y1));
+  const double rr = __dmul_rn(r0, r1);
+  if (prm.c_min > 0.0 && rr > 0.0 && rr < 1.0e300) {
+    if (dot <= rr) {
+      if (dot > __dmul_rn(prm.c_hi, rr)) { return true; }
+      if (dot < __dmul_rn(prm.c_lo, rr)) { return false; }
+    }
+  }
+  const double c = __ddiv_rn(dot, rr);
+  return (c >= prm.c_min) && (c <= 1.0);
+}
+
+// (double)(float)(|dr| / r) > rho   <=>   RN(|dr| / r) >= q_min   (host-derived q_min), guard-banded likewise
+__device__ __forceinline__ bool ratio_test(double adr, double r, const DevParams & prm)
+{
+  if (r > 0.0 && r < 1.0e300) {
+    if (adr > __dmul_rn(prm.q_hi, r)) { return true; }
+    if (adr < __dmul_rn(prm.q_lo, r)) { return false; }
+  }
+  const float q = __double2float_rn(__ddiv_rn(adr, r));  // parallel_beam.hpp:44-45
+  return (double)q > prm.rho;
+}
+
+struct OrderMap  // sorted position -> bucket position
+{
+  int mode;   // 0: start + p, 1: start - p (both mod n)
+  int start;
+  int n;
+  __device__ __forceinline__ int at(int p) const
+  {
+    int q = mode == 0 ? start + p : start - p;
+    if (q >= n) { q -= n; }
+    if (q < 0) { q += n; }
+    return q;
+  }
+};
+
+template<int PT, int TMAX, int MINB>
+__global__ void __launch_bounds__(TMAX, MINB)
+k_extract_rings2(const RingArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DevParams & prm = a.prm;
+  const int P = PT > 0 ? PT : prm.P;
+  const int B = prm.B;
+  const RingSmem2 s = carve2(smem_raw, a.cap, prm.P);
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+  const int NW = s.nwords;
+  const int data_words = a.cap / 32;
+  auto arr = [&](int k) -> uint32_t * { return s.bits + (size_t)k * NW; };
+  auto arr_bytes = [&](int k) -> uint8_t * { return reinterpret_cast<uint8_t *>(s.bits + (size_t)k * NW) + 4; };
+
+  // pad words are zero for the whole kernel; data words are rewritten for every ring
+  for (int i = tid; i < ring2_arrays(prm.P) * NW; i += T) { s.bits[i] = 0; }
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { s.misc[N_WORK] = (int)atomicAdd(&a.counters[C_WORK_NEXT], 1u); }
+    if (tid >= 1 && tid < 16) { s.misc[tid] = tid == N_POS_NONASC || tid == N_POS_ASC ? -1 : 0; }
+    for (int w = tid; w < data_words; w += T) { arr(A_SB)[1 + w] = 0; }
+    __syncthreads();
+    const uint32_t wi = (uint32_t)s.misc[N_WORK];
+    if (wi >= a.counters[C_N_WORK]) { break; }
+    const uint2 item = a.work[wi];
+    const ScanDesc sd = a.scans[item.x];
+    lfx_ring_info * ring_info = &a.rings[(size_t)item.x * a.max_rings + item.y];
+    const int n = (int)ring_info->count;
+    const uint64_t pos0 = sd.point_base + ring_info->offset;
+    const uint32_t status_in = ring_info->status;
+
+    // ---- rings that contribute nothing: sparse (ring.cpp:46-59) or over capacity
+    if (status_in != LFX_RING_OK) {
+      for (int i = tid; i < n; i += T) {
+        a.labels[pos0 + i] = LFX_LABEL_NONE;
+        if (a.sorted_src) { a.sorted_src[pos0 + i] = a.idx[pos0 + i]; }
+        if (a.curvature) { a.curvature[pos0 + i] = 0.0; }
+      }
+      if (status_in == LFX_RING_TOO_LONG && tid == 0) {
+        if (atomicExch(&a.counters[C_ERR_FLAG], LFX_E_CAPACITY) == 0) { a.counters[C_ERR_SCAN] = item.x; a.counters[C_ERR_RING] = item.y; }
+      }
+      continue;
+    }
+
+    // ---- phase 0: coalesced gather of the ring into shared memory (bucket order = source order)
+    {
+      float rx[PTS], ry[PTS];
+#pragma unroll
+      for (int m = 0; m < PTS; m++) {
+        const int q = tid + m * T;
+        rx[m] = 0.f; ry[m] = 0.f;
+        if (q < n) {
+          const uint32_t src = a.idx[pos0 + q];
+          const uint8_t * p = sd.data + (size_t)src * sd.point_step;
+          float x, y, z;
+          if (sd.vec_ok) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p + sd.off_x));
+            x = v.x; y = v.y; z = v.z;
+          } else {
+            x = *reinterpret_cast<const float *>(p + sd.off_x);
+            y = *reinterpret_cast<const float *>(p + sd.off_y);
+            z = *reinterpret_cast<const float *>(p + sd.off_z);
+          }
+          const int sl = fslot(q);
+          s.fx[sl] = x; s.fy[sl] = y; s.fz[sl] = z;
+          rx[m] = x; ry[m] = y;
+        }
+      }
+      __syncthreads();
+
+      // ---- phase 1: polar-angle order (SortByAtan2, ring.hpp:101-112). One exact comparator
+      //      evaluation per cyclic neighbour pair decides whether the ring already is a rotated
+      //      ascending (n-1 ascents) or rotated descending (<= 1 ascent) sequence.
+      int cnt = 0, pos_na = -1, pos_a = -1;
+      if (a.force_order_path == 0) {
+#pragma unroll
+        for (int m = 0; m < PTS; m++) {
+          const int q = tid + m * T;
+          if (q < n) {
+            const int q1 = q + 1 == n ? 0 : q + 1;
+            const bool asc = polar_less(rx[m], ry[m], s.fx[fslot(q1)], s.fy[fslot(q1)]);
+            cnt += asc ? 1 : 0;
+            if (asc) { pos_a = q; } else { pos_na = q; }   // q grows with m: keeps the largest
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+          pos_na = max(pos_na, __shfl_xor_sync(0xFFFFFFFFu, pos_na, o));
+          pos_a = max(pos_a, __shfl_xor_sync(0xFFFFFFFFu, pos_a, o));
+        }
+        if (lane == 0) {
+          atomicAdd(&s.misc[N_CNT_ASC], cnt);
+          atomicMax(&s.misc[N_POS_NONASC], pos_na);
+          atomicMax(&s.misc[N_POS_ASC], pos_a);
+        }
+      }
+      __syncthreads();
+    }
+    OrderMap om;
+    om.n = n;
+    int order_path = a.force_order_path;
+    if (order_path == 0) {
+      const int cnt_asc = s.misc[N_CNT_ASC];
+      if (cnt_asc == n - 1) { om.mode = 0; om.start = s.misc[N_POS_NONASC] + 1; if (om.start >= n) { om.start -= n; } }
+      else if (cnt_asc <= 1) { om.mode = 1; om.start = cnt_asc == 1 ? s.misc[N_POS_ASC] : 0; }
+      else { order_path = 1; }
+    }
+    if (order_path >= 1) {
+      int n2 = 32;
+      while (n2 < n) { n2 <<= 1; }
+      if (order_path == 1) {
+        uint32_t * keys = reinterpret_cast<uint32_t *>(s.dr - 32);  // aliases the (not yet written) range array
+        for (int i = tid; i < n2; i += T) {
+          keys[i] = i < n ? polar_key19(s.fx[fslot(i)], s.fy[fslot(i)], i) : 0xFFFFFFFFu;
+        }
+        bitonic_u32(keys, n2);
+        for (int i = tid; i < n; i += T) { s.perm[i] = (uint16_t)(keys[i] & 0x1FFFu); }
+        __syncthreads();
+        int bad = 0;  // verify with the exact comparator: no adjacent inversion
+        for (int i = tid; i + 1 < n; i += T) {
+          const int p0 = fslot(s.perm[i]), p1 = fslot(s.perm[i + 1]);
+          if (polar_less(s.fx[p1], s.fy[p1], s.fx[p0], s.fy[p0])) { bad = 1; }
+        }
+        if (__syncthreads_or(bad)) { order_path = 2; }
+      }
+      if (order_path == 2) {
+        uint16_t * pp = reinterpret_cast<uint16_t *>(s.dr - 32);  // n2 <= 8192 entries fit the range array
+        for (int i = tid; i < n2; i += T) { pp[i] = (uint16_t)i; }
+        bitonic_exact2(pp, n, n2, s.fx, s.fy);
+        for (int i = tid; i < n; i += T) { s.perm[i] = pp[i]; }
+        __syncthreads();
+      }
+      // physically reorder the coordinates so that the map becomes the identity
+      float gx[PTS], gy[PTS], gz[PTS];
+#pragma unroll
+      for (int m = 0; m < PTS; m++) {
+        const int p = tid + m * T;
+        if (p < n) { const int sl = fslot(s.perm[p]); gx[m] = s.fx[sl]; gy[m] = s.fy[sl]; gz[m] = s.fz[sl]; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < PTS; m++) {
+        const int p = tid + m * T;
+        if (p < n) { const int sl = fslot(p); s.fx[sl] = gx[m]; s.fy[sl] = gy[m]; s.fz[sl] = gz[m]; }
+      }
+      om.mode = 0; om.start = 0;
+      __syncthreads();
+    }
+
+    // ---- ring-level preconditions (the reference throws std::invalid_argument, feature_extraction.cpp:154-156)
+    bool skip = (n < 2 * P + 1) || (n - 2 * P < B);  // convolution.cpp:39-43, index_range.cpp:35-40
+    if (!skip) {
+      if (tid <= B) {  // IndexRange::Boundary index_range.cpp:60-66, evaluated without contraction
+        const double sdb = (double)P, edb = (double)(n - P), nb = (double)B, j = (double)tid;
+        const double t1 = __dmul_rn(sdb, __dsub_rn(1.0, __ddiv_rn(j, nb)));
+        const double t2 = __ddiv_rn(__dmul_rn(edb, j), nb);
+        s.bnd[tid] = (int)__dadd_rn(t1, t2);
+      }
+      __syncthreads();
+      int bad = 0;
+      if (tid < B) {
+        if (s.bnd[tid + 1] - s.bnd[tid] < 2) { bad = 1; }  // Slice -> NeighborCheckXY ctor, neighbor.hpp:71-75
+        const int last = s.bnd[tid + 1] - 1;                // last position of sector tid
+        if (last >= 0) { atomicOr(&arr(A_SB)[1 + (last >> 5)], 1u << (last & 31)); }
+      }
+      skip = __syncthreads_or(bad) != 0;
+    }
+
+    const int p0 = PTS * tid;
+    // ---- phase 2: XY range in double (Range, range.hpp:52-56; XYNorm math.hpp:36-39) for the 8 owned points
+    float xk[PTS + 1], yk[PTS + 1];
+    double rk[PTS];
+    if (!skip) {
+#pragma unroll
+      for (int k = 0; k <= PTS; k++) {
+        const int p = p0 + k;
+        xk[k] = 0.f; yk[k] = 0.f;
+        if (p < n) { const int sl = fslot(om.at(p)); xk[k] = s.fx[sl]; yk[k] = s.fy[sl]; }
+      }
+#pragma unroll
+      for (int k = 0; k < PTS; k++) {
+        const double xd = (double)xk[k], yd = (double)yk[k];
+        rk[k] = __dsqrt_rn(__dadd_rn(__dmul_rn(xd, xd), __dmul_rn(yd, yd)));
+        s.dr[dslot(p0 + k)] = rk[k];
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 3: per-point predicates as bytes of bit streams, curvature in a register window
+    if (!skip) {
+      constexpr int PM = PT > 0 ? PT : MAX_PADDING;
+      // XY range of positions p0 - P .. p0 + 8 + 2P - 1  (index j + P)
+      double rw[PTS + 3 * PM];
+#pragma unroll
+      for (int j = -PM; j < PTS + 2 * PM; j++) {
+        if (j >= -P && j < PTS + 2 * P) { rw[j + PM] = (j >= 0 && j < PTS) ? rk[j] : s.dr[dslot(p0 + j)]; }
+      }
+      uint32_t b_link = 0, b_ls = 0, b_tl = 0, b_trs = 0, b_oor = 0, b_pb = 0, b_e = 0, b_s0 = 0;
+      const uint32_t sb = arr_bytes(A_SB)[tid];
+      int zero_pair = 0;
+#pragma unroll
+      for (int k = 0; k < PTS; k++) {
+        const int p = p0 + k;
+        const double r0 = rw[k + PM], r1 = rw[k + 1 + PM], rm = rw[k - 1 + PM];
+        if (p + 1 < n) {
+          if (r0 == 0.0 && r1 == 0.0) { zero_pair = 1; }  // CalcRadian throws, math.cpp:40-42
+          const bool link = link_test((double)xk[k], (double)yk[k], (double)xk[k + 1], (double)yk[k + 1], r0, r1, prm);
+          if (link) {
+            b_link |= 1u << k;
+            if (p >= P && p + 1 < n - P && !((sb >> k) & 1u)) { b_ls |= 1u << k; }
+            if (p < n - P - 1 && r1 > __dadd_rn(r0, prm.d)) { b_tl |= 1u << k; }       // occlusion.hpp:45-53
+            if (p + 1 >= P + 1 && r0 > __dadd_rn(r1, prm.d)) { b_trs |= 1u << k; }     // occlusion.hpp:67-75
+          }
+        }
+        if (p < n) {
+          if (!(prm.rmin <= r0 && r0 <= prm.rmax)) { b_oor |= 1u << k; }              // out_of_range.hpp:36-48
+          if (p >= 1 && p <= n - 2) {                                                    // parallel_beam.hpp:36-51
+            if (ratio_test(fabs(__dsub_rn(rm, r0)), r0, prm) && ratio_test(fabs(__dsub_rn(r1, r0)), r0, prm)) { b_pb |= 1u << k; }
+          }
+        }
+      }
+      // curvature of positions p0 .. p0 + 8 + P - 1 (CalcCurvature curvature.cpp:44-50: sum left to right
+      // from 0.0, centre weight -2P, uncontracted); C_d bits as soon as both operands exist
+      double cw[PTS + PM];
+      uint32_t b_c[PM];
+#pragma unroll
+      for (int d = 0; d < PM; d++) { b_c[d] = 0; }
+#pragma unroll
+      for (int j = 0; j < PTS + PM; j++) {
+        if (j < PTS + P) {
+          const int p = p0 + j;
+          double cv = 0.0;
+          if (p >= P && p < n - P) {
+            double sum = rw[j - P + PM];
+#pragma unroll
+            for (int m = -PM + 1; m <= PM; m++) {
+              if (m > -P && m <= P) { sum = __dadd_rn(sum, m == 0 ? __dmul_rn(rw[j + PM], prm.center_w) : rw[j + m + PM]); }
+            }
+            cv = __dmul_rn(sum, sum);
+          }
+          cw[j] = cv;
+          if (j < PTS) {
+            if (p >= P && p < n - P) {
+              if (cv >= prm.tau_e) { b_e |= 1u << j; }
+              if (cv <= prm.tau_s) { b_s0 |= 1u << j; }
+            }
+            if (a.curvature && p < n) { a.curvature[pos0 + p] = cv; }
+          }
+#pragma unroll
+          for (int d = 1; d <= PM; d++) {
+            if (d <= P && j - d >= 0 && j - d < PTS) { if (cv >= cw[j - d]) { b_c[d - 1] |= 1u << (j - d); } }
+          }
+        }
+      }
+      arr_bytes(A_LINK)[tid] = (uint8_t)b_link;
+      arr_bytes(A_LS)[tid] = (uint8_t)b_ls;
+      arr_bytes(A_TL)[tid] = (uint8_t)b_tl;
+      arr_bytes(A_TRS)[tid] = (uint8_t)b_trs;
+      arr_bytes(A_OOR)[tid] = (uint8_t)b_oor;
+      arr_bytes(A_PB)[tid] = (uint8_t)b_pb;
+      arr_bytes(A_E)[tid] = (uint8_t)b_e;
+      arr_bytes(A_S0)[tid] = (uint8_t)b_s0;
+#pragma unroll
+      for (int d = 0; d < PM; d++) { if (d < P) { arr_bytes(A_C0 + d)[tid] = (uint8_t)b_c[d]; } }
+      if (zero_pair) { s.misc[N_SKIP] = 1; }
+    }
+    __syncthreads();
+    if (!skip && s.misc[N_SKIP]) { skip = true; }
+
+    if (skip) {
+      for (int i = tid; i < n; i += T) {
+        a.labels[pos0 + i] = LFX_LABEL_NONE;
+        if (a.sorted_src) { a.sorted_src[pos0 + i] = a.idx[pos0 + (order_path >= 1 ? (int)s.perm[i] : om.at(i))]; }
+        if (a.curvature) { a.curvature[pos0 + i] = 0.0; }
+      }
+      if (tid == 0) { ring_info->status = LFX_RING_SKIPPED; ring_info->order_path = order_path; }
+      continue;
+    }
+
+    // ---- phase 4: bit-sliced selection, one thread per 32-position word.
+    //      The greedy walk of label.hpp:85-94 / 124-133 over the (value, index)-sorted order is the
+    //      lexicographically-first maximal independent set of the symmetric cover relation
+    //      (fill.hpp:101-117 clipped to the sector), i.e. the unique solution of
+    //          x_i = cand_i && !exists j in window(i): key(j) before key(i) && x_j
+    //      (dependencies are acyclic by key order), reached by chaotic iteration from x = 0.
+    {
+      constexpr int PM = PT > 0 ? PT : MAX_PADDING;
+      const int w = tid;
+      const bool active = w < data_words;
+      uint32_t gp[PM], gm[PM], sp[PM], sm[PM], vp[PM], vm[PM];
+      uint32_t cand_e = 0, cand_s0 = 0;
+      if (active) {
+        const uint32_t * LS = arr(A_LS);
+        const uint32_t lsm = LS[w], ls0 = LS[w + 1], lsp = LS[w + 2];  // words w-1, w, w+1
+        uint32_t v_prev = 0xFFFFFFFFu, v_cur = 0xFFFFFFFFu;           // V_0 = all ones
+#pragma unroll
+        for (int d = 1; d <= PM; d++) {
+          if (d <= P) {
+            // V_d(i) = V_{d-1}(i) & LS(i + d - 1): all links between i and i+d usable
+            v_cur &= d == 1 ? ls0 : shr_bits(ls0, lsp, d - 1);
+            v_prev &= d == 1 ? lsm : shr_bits(lsm, ls0, d - 1);
+            const uint32_t * C = arr(A_C0 + d - 1);
+            const uint32_t c_prev = C[w], c_cur = C[w + 1];
+            const uint32_t a_cur = c_cur & v_cur, a_prev = c_prev & v_prev;     // key(i+d) > key(i), in window
+            const uint32_t b_cur = ~c_cur & v_cur, b_prev = ~c_prev & v_prev;   // key(i+d) < key(i), in window
+            gp[d - 1] = a_cur;                             // edge pass: i+d dominates i
+            gm[d - 1] = shl_bits(b_prev, b_cur, d);        // edge pass: i-d dominates i  <=>  key(i) < key(i-d)
+            sp[d - 1] = b_cur;                             // surface pass: smaller keys dominate
+            sm[d - 1] = shl_bits(a_prev, a_cur, d);
+            vp[d - 1] = v_cur;
+            vm[d - 1] = shl_bits(v_prev, v_cur, d);
+          }
+        }
+        cand_e = arr(A_E)[w + 1];
+        cand_s0 = arr(A_S0)[w + 1];
+      }
+      uint32_t * XE = arr(A_XE), * XS = arr(A_XS);
+      if (active) { XE[w + 1] = 0; XS[w + 1] = 0; }
+      __syncthreads();
+      // edge pass
+      for (;;) {
+        int changed = 0;
+        if (active) {
+          const uint32_t xl = XE[w], xc = XE[w + 1], xr = XE[w + 2];
+          uint32_t blocked = 0;
+#pragma unroll
+          for (int d = 1; d <= PM; d++) {
+            if (d <= P) { blocked |= (gp[d - 1] & shr_bits(xc, xr, d)) | (gm[d - 1] & shl_bits(xl, xc, d)); }
+          }
+          const uint32_t xn = cand_e & ~blocked;
+          if (xn != xc) { XE[w + 1] = xn; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) { break; }
+      }
+      uint32_t xe = 0, ce = 0;
+      if (active) {
+        const uint32_t xl = XE[w], xc = XE[w + 1], xr = XE[w + 2];
+        xe = xc; ce = xc;
+#pragma unroll
+        for (int d = 1; d <= PM; d++) {
+          if (d <= P) { ce |= (vp[d - 1] & shr_bits(xc, xr, d)) | (vm[d - 1] & shl_bits(xl, xc, d)); }
+        }
+      }
+      const uint32_t cand_s = cand_s0 & ~ce;   // still Default after the edge pass, label.hpp:125
+      // surface pass
+      for (;;) {
+        int changed = 0;
+        if (active) {
+          const uint32_t xl = XS[w], xc = XS[w + 1], xr = XS[w + 2];
+          uint32_t blocked = 0;
+#pragma unroll
+          for (int d = 1; d <= PM; d++) {
+            if (d <= P) { blocked |= (sp[d - 1] & shr_bits(xc, xr, d)) | (sm[d - 1] & shl_bits(xl, xc, d)); }
+          }
+          const uint32_t xn = cand_s & ~blocked;
+          if (xn != xc) { XS[w + 1] = xn; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) { break; }
+      }
+      // ---- phase 5: covers, occlusion fills, label priority - all per word
+      if (active) {
+        const uint32_t xl = XS[w], xc = XS[w + 1], xr = XS[w + 2];
+        uint32_t cs = xc;
+#pragma unroll
+        for (int d = 1; d <= PM; d++) {
+          if (d <= P) { cs |= (vp[d - 1] & shr_bits(xc, xr, d)) | (vm[d - 1] & shl_bits(xl, xc, d)); }
+        }
+        // occlusion (occlusion.hpp:37-91): a trigger within P+1 positions whose chain of links reaches i
+        const uint32_t * LK = arr(A_LINK), * TL = arr(A_TL), * TRS = arr(A_TRS);
+        const uint32_t lkm = LK[w], lk0 = LK[w + 1], lkp = LK[w + 2];
+        const uint32_t tlm = TL[w], tl0 = TL[w + 1], tr0 = TRS[w + 1], trp = TRS[w + 2];
+        uint32_t occ = 0, ch = 0xFFFFFFFFu, chr = 0xFFFFFFFFu;
+#pragma unroll
+        for (int m = 0; m <= PM; m++) {
+          if (m <= P) {
+            occ |= ch & shl_bits(tlm, tl0, m + 1);                 // TL(i-1-m) & LINK(i-1..i-m)
+            ch &= shl_bits(lkm, lk0, m + 1);
+            occ |= chr & (m == 0 ? tr0 : shr_bits(tr0, trp, m));   // TRS(i+m) & LINK(i..i+m-1)
+            chr &= m == 0 ? lk0 : shr_bits(lk0, lkp, m);
+          }
+        }
+        // final label = ParallelBeam > OutOfRange > Occluded > selection (feature_extraction.cpp:133-138)
+        const uint32_t pb = arr(A_PB)[w + 1], oor = arr(A_OOR)[w + 1];
+        const uint32_t m7 = pb, m5 = oor & ~pb, m6 = occ & ~oor & ~pb, rest = ~(pb | oor | occ);
+        const uint32_t m1 = xe & rest, m3 = xc & ~xe & rest, m4 = cs & ~xc & ~xe & rest, m2 = ce & ~xe & ~cs & rest;
+        arr(A_L0)[w + 1] = m7 | m5 | m1 | m3;
+        arr(A_L1)[w + 1] = m7 | m6 | m3 | m2;
+        arr(A_L2)[w + 1] = m7 | m5 | m6 | m4;
+        arr(A_EM)[w + 1] = m1;
+        arr(A_SM)[w + 1] = m3;
+        s.wpre[w] = __popc(m1);
+        s.wpre[NW + w] = __popc(m3);
+      }
+      __syncthreads();
+      // exclusive prefix of the per-word counts: warp 0 for Edge, warp 1 for Surface
+      if (tid < 64) {
+        uint32_t * c = s.wpre + (tid >> 5) * NW;
+        const int per = (data_words + 31) / 32;
+        const int b0 = lane * per;
+        uint32_t sum = 0;
+        for (int k = 0; k < per; k++) { if (b0 + k < data_words) { sum += c[b0 + k]; } }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) { inc += v; } }
+        uint32_t run = inc - sum;
+        for (int k = 0; k < per; k++) { if (b0 + k < data_words) { const uint32_t v = c[b0 + k]; c[b0 + k] = run; run += v; } }
+        if (lane == 31) { if (tid < 32) { ring_info->n_edge = inc; } else { ring_info->n_surface = inc; } }
+      }
+      __syncthreads();
+    }
+
+    // ---- phase 6: outputs. Label bytes (8 per thread), feature points staged (edge ascending from the
+    //      ring start, surface descending from the ring end).
+    if (p0 < n) {
+      uint32_t l0lo, l0hi, l1lo, l1hi, l2lo, l2hi;
+      spread8(arr_bytes(A_L0)[tid], l0lo, l0hi);
+      spread8(arr_bytes(A_L1)[tid], l1lo, l1hi);
+      spread8(arr_bytes(A_L2)[tid], l2lo, l2hi);
+      const uint32_t lo = l0lo | (l1lo << 1) | (l2lo << 2), hi = l0hi | (l1hi << 1) | (l2hi << 2);
+      uint8_t * dst = a.labels + pos0 + p0;
+      if (p0 + PTS <= n && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(lo, hi);
+      } else {
+#pragma unroll
+        for (int k = 0; k < PTS; k++) { if (p0 + k < n) { dst[k] = (uint8_t)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFFu); } }
+      }
+      const int w = tid >> 2, sh = (tid & 3) * 8;
+      uint32_t em = arr_bytes(A_EM)[tid], smk = arr_bytes(A_SM)[tid];
+      if (em | smk) {
+        uint32_t re = s.wpre[w] + __popc(arr(A_EM)[w + 1] & ((1u << sh) - 1u));
+        uint32_t rs = s.wpre[NW + w] + __popc(arr(A_SM)[w + 1] & ((1u << sh) - 1u));
+        while (em) {
+          const int k = __ffs(em) - 1; em &= em - 1;
+          const int sl = fslot(om.at(p0 + k));
+          a.stage[pos0 + re++] = make_float4(s.fx[sl], s.fy[sl], s.fz[sl], 1.0f);
+        }
+        while (smk) {
+          const int k = __ffs(smk) - 1; smk &= smk - 1;
+          const int sl = fslot(om.at(p0 + k));
+          a.stage[pos0 + (uint32_t)(n - 1) - rs++] = make_float4(s.fx[sl], s.fy[sl], s.fz[sl], 1.0f);
+        }
+      }
+    }
+    if (a.sorted_src) {
+      for (int i = tid; i < n; i += T) { a.sorted_src[pos0 + i] = a.idx[pos0 + (order_path >= 1 ? (int)s.perm[i] : om.at(i))]; }
+    }
+    if (tid == 0) { ring_info->order_path = order_path; }
+  }
+}
+
+}  // namespace lfxk
+#endif  // LFX_RING_CUH_
