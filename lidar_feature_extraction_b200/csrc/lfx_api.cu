@@ -70,6 +70,8 @@ struct lfx_handle
   DevBuf<lfx_ring_info> d_rings;
   DevBuf<uint2> d_work;
   DevBuf<uint2> d_ring_featoff;
+  DevBuf<uint2> d_ring_src;
+  DevBuf<uint32_t> d_scan_flags;
   DevBuf<uint32_t> d_idx;
   DevBuf<uint8_t> d_labels;
   DevBuf<uint32_t> d_sorted_src;
@@ -176,10 +178,10 @@ double ratio_cut(double rho)
 template<int PT>
 void (*pick_ring_kernel_t(int threads, int * tmax))(const RingArgs)
 {
-  if (threads <= 288) { *tmax = 288; return k_extract_rings2<PT, 288, 3>; }
-  if (threads <= 512) { *tmax = 512; return k_extract_rings2<PT, 512, 1>; }
+  if (threads <= 288) { *tmax = 288; return k_extract_rings<PT, 288, 2>; }
+  if (threads <= 512) { *tmax = 512; return k_extract_rings<PT, 512, 1>; }
   *tmax = 1024;
-  return k_extract_rings2<PT, 1024, 1>;
+  return k_extract_rings<PT, 1024, 1>;
 }
 
 void (*pick_ring_kernel(int padding, int threads, int * tmax))(const RingArgs)
@@ -214,7 +216,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       h->d_scans.p, n_scans, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
   }
   k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
-    h->d_scans.p, h->d_tile_hist.p, h->d_rings.p, h->d_work.p, h->d_counters, max_rings, h->params.padding, h->cap);
+    h->d_scans.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, h->d_work.p, h->d_counters, max_rings, h->params.padding, h->cap);
   if (n_tiles > 0) {
     k_ring_scatter<<<n_tiles, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
       h->d_scans.p, n_scans, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
@@ -224,6 +226,8 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   ra.scans = h->d_scans.p;
   ra.idx = h->d_idx.p;
   ra.rings = h->d_rings.p;
+  ra.ring_src = h->d_ring_src.p;
+  ra.scan_flags = h->d_scan_flags.p;
   ra.work = h->d_work.p;
   ra.counters = h->d_counters;
   ra.labels = h->d_labels.p;
@@ -345,7 +349,7 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->dev.center_w = -2. * params->padding;  // MakeWeight curvature.cpp:40
 
   // kernel attributes / persistent grid sizes
-  h->ring_smem = ring2_smem_bytes(h->cap, params->padding);
+  h->ring_smem = ring_smem_bytes(h->cap, params->padding);
   if (h->ring_smem > (size_t)prop.sharedMemPerBlockOptin) {
     g_create_error = "max_ring_points does not fit in shared memory";
     lfx_destroy(h);
@@ -380,7 +384,7 @@ void lfx_destroy(lfx_handle * h)
   if (h->stream) { cudaStreamSynchronize(h->stream); }
   drop_graphs(h);
   cudaFree(h->d_scans.p); cudaFree(h->d_point_base.p); cudaFree(h->d_ring16.p); cudaFree(h->d_tile_hist.p);
-  cudaFree(h->d_rings.p); cudaFree(h->d_work.p); cudaFree(h->d_ring_featoff.p); cudaFree(h->d_idx.p);
+  cudaFree(h->d_rings.p); cudaFree(h->d_work.p); cudaFree(h->d_ring_featoff.p); cudaFree(h->d_ring_src.p); cudaFree(h->d_scan_flags.p); cudaFree(h->d_idx.p);
   cudaFree(h->d_labels.p); cudaFree(h->d_sorted_src.p); cudaFree(h->d_curv.p); cudaFree(h->d_stage.p);
   cudaFree(h->d_edge.p); cudaFree(h->d_surface.p); cudaFree(h->d_counts.p); cudaFree(h->d_offsets.p);
   cudaFree(h->d_input.p); cudaFree(h->d_counters);
@@ -446,6 +450,8 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
   if ((rc = ensure(h, h->d_rings, ns * mr, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_work, ns * mr, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_ring_featoff, ns * mr, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_ring_src, ns * mr, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_scan_flags, ns, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_idx, np, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_labels, np, &regrown))) { return rc; }
   if (h->opt.want_sorted_src && (rc = ensure(h, h->d_sorted_src, np, &regrown))) { return rc; }
@@ -504,6 +510,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
     d.ring_dt = v.ring_datatype;
     d.tile_base = tb;
     d.n_tiles = (v.n_points + TILE - 1) / TILE;
+    d.reserved[0] = d.reserved[1] = 0;
     d.vec_ok = (v.off_y == v.off_x + 4 && v.off_z == v.off_x + 8 && v.off_x % 16 == 0 && v.point_step % 16 == 0 &&
                 v.off_x + 16 <= v.point_step && reinterpret_cast<uintptr_t>(d.data) % 16 == 0) ? 1u : 0u;
     h->h_point_base[s] = pb;

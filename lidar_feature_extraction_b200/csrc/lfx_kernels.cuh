@@ -41,6 +41,7 @@ struct ScanDesc
   uint32_t tile_base;   // first ingest tile of this scan
   uint32_t n_tiles;
   uint32_t vec_ok;      // xyz loadable as one aligned float4
+  uint32_t reserved[2]; // pads the descriptor to 64 bytes (copied with 16-byte cp.async)
 };
 
 struct DevParams
@@ -61,6 +62,8 @@ struct RingArgs
   const ScanDesc * scans;
   const uint32_t * idx;        // [total_points] bucketed source indices
   lfx_ring_info * rings;       // [n_scans][max_rings]
+  const uint2 * ring_src;      // [n_scans][max_rings] (first, stride) of rings laid out regularly; stride 0 => idx list
+  uint32_t * scan_flags;       // [n_scans] bit 0: the regular-layout hypothesis failed, redo through the general ingest
   const uint2 * work;          // (scan, ring)
   uint32_t * counters;
   uint8_t * labels;
@@ -160,7 +163,7 @@ k_ring_hist(const ScanDesc * __restrict__ scans, int n_scans, uint16_t * __restr
 
 __global__ void __launch_bounds__(256)
 k_ring_plan(const ScanDesc * __restrict__ scans, uint32_t * __restrict__ tile_hist, lfx_ring_info * __restrict__ rings,
-            uint2 * __restrict__ work, uint32_t * counters, int max_rings, int padding, int cap)
+            uint2 * __restrict__ ring_src, uint2 * __restrict__ work, uint32_t * counters, int max_rings, int padding, int cap)
 {
   extern __shared__ uint32_t s_cnt[];  // [max_rings] counts, then [max_rings] offsets
   uint32_t * s_off = s_cnt + max_rings;
@@ -194,6 +197,7 @@ k_ring_plan(const ScanDesc * __restrict__ scans, uint32_t * __restrict__ tile_hi
     ri.status = ri.count == 0 ? LFX_RING_OK : (ri.count < (uint32_t)(padding + 1) ? LFX_RING_SPARSE : (ri.count > (uint32_t)cap ? LFX_RING_TOO_LONG : LFX_RING_OK));
     ri.order_path = 0;
     rings[(size_t)scan * max_rings + r] = ri;
+    ring_src[(size_t)scan * max_rings + r] = make_uint2(0u, 0u);  // addressed through the bucketed index list
   }
   if (threadIdx.x == 0 && s_n_present) {
     uint32_t k = s_work_base;

@@ -1,14 +1,16 @@
-// lfx_ring.cuh — the per-ring kernel (v2): everything in feature_extraction.cpp:121-151 for one ring,
-// held in shared memory by one CTA.
+// lfx_ring.cuh — the per-ring kernel: everything in feature_extraction.cpp:121-151 for one ring, held in
+// shared memory by one CTA; a persistent grid walks the (scan, ring) work list.
 //
-// Shape of the computation (why it looks the way it does):
-//  * the kernel is instruction-issue bound, not DRAM bound (profiles/r01a): so every thread owns EIGHT
-//    consecutive ring positions, keeps the XY-range / curvature sliding windows in registers, and writes
-//    each per-point predicate as one BYTE of a bit stream (no ballots, no per-point smem round trips);
-//  * everything that is a neighbourhood predicate (conflict windows, greedy selection, cover fills,
-//    occlusion fills, label priority) then runs bit-sliced on 32-point words: one thread per word,
-//    ~1 instruction per point per sweep.
-//  * all roundings that decide a label are IEEE-exact and uncontracted; divisions are replaced by
+// Shape of the computation (why it looks the way it does; evidence in profiles/):
+//  * The path is instruction-issue / latency bound, not DRAM bound. So every thread owns EIGHT consecutive
+//    ring positions, keeps the XY-range / curvature sliding windows in registers, and writes each
+//    per-point predicate as one BYTE of a bit stream (no ballots, no per-point shared-memory round trips).
+//  * Everything that is a neighbourhood predicate (conflict windows, greedy selection, cover fills,
+//    occlusion fills, label priority) runs bit-sliced on 32-position words: one thread per word.
+//  * Global latency is taken off the critical path: the xyz of ring k+1 are fetched with cp.async
+//    (16 B per point, L1-bypassing) into the second half of a double buffer while ring k is processed;
+//    the (scan, ring) descriptors are themselves prefetched two rings ahead with cp.async.
+//  * All roundings that decide a label are IEEE-exact and uncontracted; divisions are replaced by
 //    guard-banded multiplications with an exact fallback inside the band.
 #ifndef LFX_RING_CUH_
 #define LFX_RING_CUH_
@@ -30,7 +32,7 @@ enum BitArray {
   A_PB,        // parallel beam                                          parallel_beam.hpp:36-51
   A_E,         // edge candidate: inside && curvature >= edge_threshold  label.hpp:81-83
   A_S0,        // surface candidate before the edge pass: inside && curvature <= surface_threshold
-  A_SB,        // i is the last position of a sector (or outside [P, n-P-1))
+  A_SB,        // i is the last position of a sector
   A_XE,        // picked Edge
   A_XS,        // picked Surface
   A_L0, A_L1, A_L2,  // bit planes of the final label
@@ -39,57 +41,69 @@ enum BitArray {
   A_COUNT_FIXED = A_C0
 };
 
-struct RingSmem2
+// what one ring needs, assembled in shared memory by cp.async two rings ahead
+struct RingMeta
 {
-  float * fx, * fy, * fz;   // bucket-order coordinates, padded: slot(q) = q + (q >> 5)
-  double * dr;              // XY range by sorted position, padded: slot(p) = p + (p >> 4), halo of 32 each side
+  ScanDesc sd;          // 64 B
+  lfx_ring_info info;   // 24 B
+  uint2 src;            // (first, stride); stride 0 => bucketed index list
+};
+static_assert(sizeof(ScanDesc) == 64, "ScanDesc is copied in 16-byte pieces");
+static_assert(sizeof(lfx_ring_info) == 24, "lfx_ring_info is copied in 8-byte pieces");
+static_assert(sizeof(RingMeta) == 96, "RingMeta layout");
+
+struct RingSmem
+{
+  float4 * pts[2];          // double-buffered xyz(+pad), bucket order, XOR-swizzled: slot(q) = q ^ ((q >> 3) & 7)
+  double * dr;              // XY range by sorted position, padded: slot(p) = p + (p >> 4), halo of 32 in front
   uint32_t * bits;          // [n_arrays][nwords] ; word 0 of each array is a zero pad
   uint32_t * wpre;          // [2][nwords] exclusive prefix of per-word Edge / Surface counts
   uint16_t * perm;          // [cap] sorted position -> bucket position (sort path only)
+  RingMeta * meta;          // [3]
+  uint2 * items;            // [4]
   int * bnd;                // [MAX_BLOCKS + 1]
   int * misc;               // [16]
   int nwords;               // words per bit array = cap / 32 + 4
 };
 
-__host__ __device__ inline int ring2_arrays(int P) { return A_COUNT_FIXED + P; }
+__host__ __device__ inline int ring_arrays(int P) { return A_COUNT_FIXED + P; }
 
-__host__ __device__ inline size_t ring2_smem_bytes(int cap, int P)
+__host__ __device__ inline size_t ring_smem_bytes(int cap, int P)
 {
   const int nwords = cap / 32 + 4;
   size_t b = 0;
-  b += (size_t)(cap + cap / 32 + 8) * 4 * 3;        // fx, fy, fz
+  b += (size_t)cap * 16 * 2;                        // pts[2]
   b += (size_t)(cap + cap / 16 + 128) * 8;          // dr (+ halo)
-  b += (size_t)ring2_arrays(P) * nwords * 4;        // bit streams
+  b += (size_t)ring_arrays(P) * nwords * 4;         // bit streams
   b += (size_t)2 * nwords * 4;                      // wpre
   b += (size_t)cap * 2;                             // perm
-  b += (MAX_BLOCKS + 1) * 4 + 16 * 4;
+  b += 3 * sizeof(RingMeta) + 4 * sizeof(uint2);
+  b += (MAX_BLOCKS + 1 + 3) / 4 * 16 + 16 * 4;
   return (b + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ RingSmem2 carve2(unsigned char * base, int cap, int P)
+__device__ __forceinline__ RingSmem carve_ring(unsigned char * base, int cap, int P)
 {
-  RingSmem2 s;
+  RingSmem s;
   s.nwords = cap / 32 + 4;
-  const size_t fl = (size_t)(cap + cap / 32 + 8);
+  s.pts[0] = reinterpret_cast<float4 *>(base); base += (size_t)cap * 16;
+  s.pts[1] = reinterpret_cast<float4 *>(base); base += (size_t)cap * 16;
   s.dr = reinterpret_cast<double *>(base) + 32; base += (size_t)(cap + cap / 16 + 128) * 8;
-  s.fx = reinterpret_cast<float *>(base); base += fl * 4;
-  s.fy = reinterpret_cast<float *>(base); base += fl * 4;
-  s.fz = reinterpret_cast<float *>(base); base += fl * 4;
-  s.bits = reinterpret_cast<uint32_t *>(base); base += (size_t)ring2_arrays(P) * s.nwords * 4;
+  s.meta = reinterpret_cast<RingMeta *>(base); base += 3 * sizeof(RingMeta);
+  s.items = reinterpret_cast<uint2 *>(base); base += 4 * sizeof(uint2);
+  s.bits = reinterpret_cast<uint32_t *>(base); base += (size_t)ring_arrays(P) * s.nwords * 4;
   s.wpre = reinterpret_cast<uint32_t *>(base); base += (size_t)2 * s.nwords * 4;
-  s.bnd = reinterpret_cast<int *>(base); base += (MAX_BLOCKS + 1) * 4;
+  s.bnd = reinterpret_cast<int *>(base); base += (MAX_BLOCKS + 1 + 3) / 4 * 16;
   s.misc = reinterpret_cast<int *>(base); base += 16 * 4;
   s.perm = reinterpret_cast<uint16_t *>(base);
   return s;
 }
 
-enum Misc2 { N_WORK = 0, N_CNT_ASC = 1, N_POS_NONASC = 2, N_POS_ASC = 3, N_SKIP = 4 };
+enum Misc { N_CNT_ASC = 1, N_POS_NONASC = 2, N_POS_ASC = 3, N_SKIP = 4, N_BADRING = 5 };
 
-__device__ __forceinline__ int fslot(int q) { return q + (q >> 5); }
+__device__ __forceinline__ int pslot(int q) { return q ^ ((q >> 3) & 7); }
 __device__ __forceinline__ int dslot(int p) { return p + (p >> 4); }
 
-// word helpers on a bit stream X (pointer to its word 0 = front pad): data word w is X[1 + w]
-__device__ __forceinline__ uint32_t wd(const uint32_t * X, int w) { return X[1 + w]; }
 // bit j of result = X(32 w + j + k), 0 <= k < 32
 __device__ __forceinline__ uint32_t shr_bits(uint32_t cur, uint32_t next, int k) { return __funnelshift_r(cur, next, k); }
 // bit j of result = X(32 w + j - k), 1 <= k < 32
@@ -100,6 +114,28 @@ __device__ __forceinline__ void spread8(uint32_t b, uint32_t & lo, uint32_t & hi
 {
   lo = ((b & 0xFu) * 0x00204081u) & 0x01010101u;
   hi = (((b >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void * smem_dst, const void * gsrc)
+{
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// OR-reducing barrier over the first `nthreads` threads (multiple of 32) on hardware barrier 1
+__device__ __forceinline__ int bar1_or(int pred, int nthreads)
+{
+  int res;
+  asm volatile(
+    "{ .reg .pred p, q; setp.ne.s32 q, %1, 0; barrier.red.or.pred p, 1, %2, q; selp.s32 %0, 1, 0, p; }"
+    : "=r"(res) : "r"(pred), "r"(nthreads) : "memory");
+  return res;
 }
 
 // 32-bit (19-bit pseudo angle | 13-bit position) sort key for the non-monotone path
@@ -125,8 +161,8 @@ __device__ __forceinline__ void bitonic_u32(uint32_t * k, int n2)
   __syncthreads();
 }
 
-// exact fallback: bitonic sort of bucket positions with the reference comparator (padded coordinate arrays)
-__device__ __forceinline__ void bitonic_exact2(uint16_t * p, int n, int n2, const float * fx, const float * fy)
+// exact fallback: bitonic sort of bucket positions with the reference comparator
+__device__ __forceinline__ void bitonic_exact(uint16_t * p, int n, int n2, const float4 * pts)
 {
   for (int size = 2; size <= n2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -138,9 +174,12 @@ __device__ __forceinline__ void bitonic_exact2(uint16_t * p, int n, int n2, cons
         const int a = p[lo], b = p[hi];
         bool a_after_b;
         if (a >= n || b >= n) { a_after_b = a > b; }
-        else if (polar_less(fx[fslot(b)], fy[fslot(b)], fx[fslot(a)], fy[fslot(a)])) { a_after_b = true; }
-        else if (polar_less(fx[fslot(a)], fy[fslot(a)], fx[fslot(b)], fy[fslot(b)])) { a_after_b = false; }
-        else { a_after_b = a > b; }
+        else {
+          const float4 pa = pts[pslot(a)], pb = pts[pslot(b)];
+          if (polar_less(pb.x, pb.y, pa.x, pa.y)) { a_after_b = true; }
+          else if (polar_less(pa.x, pa.y, pb.x, pb.y)) { a_after_b = false; }
+          else { a_after_b = a > b; }
+        }
         if (a_after_b == up) { p[lo] = (uint16_t)b; p[hi] = (uint16_t)a; }
       }
     }
@@ -190,109 +229,184 @@ struct OrderMap  // sorted position -> bucket position
   }
 };
 
+// source point index of bucket position q of a ring
+__device__ __forceinline__ uint32_t src_index(const RingArgs & a, const RingMeta & m, uint64_t pos0, int q)
+{
+  return m.src.y ? m.src.x + (uint32_t)q * m.src.y : a.idx[pos0 + q];
+}
+
+// descriptors of work item `w`: the (scan, ring) pair must already sit in s.items[w & 3]
+__device__ __forceinline__ void prefetch_meta(const RingArgs & a, const RingSmem & s, uint32_t w)
+{
+  const uint2 item = s.items[w & 3];
+  RingMeta * m = &s.meta[w % 3];
+  const char * sd = reinterpret_cast<const char *>(&a.scans[item.x]);
+  cp_async16(reinterpret_cast<char *>(&m->sd), sd);
+  cp_async16(reinterpret_cast<char *>(&m->sd) + 16, sd + 16);
+  cp_async16(reinterpret_cast<char *>(&m->sd) + 32, sd + 32);
+  cp_async16(reinterpret_cast<char *>(&m->sd) + 48, sd + 48);
+  const size_t k = (size_t)item.x * a.max_rings + item.y;
+  const char * ri = reinterpret_cast<const char *>(&a.rings[k]);
+  cp_async8(reinterpret_cast<char *>(&m->info), ri);
+  cp_async8(reinterpret_cast<char *>(&m->info) + 8, ri + 8);
+  cp_async8(reinterpret_cast<char *>(&m->info) + 16, ri + 16);
+  cp_async8(&m->src, &a.ring_src[k]);
+}
+
+// asynchronous gather of one ring's xyz into a staging buffer (bucket order = source order)
+__device__ __forceinline__ void issue_ring_loads(const RingArgs & a, const RingMeta & m, float4 * buf, int tid, int T)
+{
+  if (m.info.status != LFX_RING_OK) { return; }
+  const int n = (int)m.info.count;
+  const uint64_t pos0 = m.sd.point_base + m.info.offset;
+#pragma unroll
+  for (int k = 0; k < PTS; k++) {
+    const int q = tid + k * T;
+    if (q < n) {
+      const uint8_t * p = m.sd.data + (size_t)src_index(a, m, pos0, q) * m.sd.point_step;
+      if (m.sd.vec_ok) {
+        cp_async16(&buf[pslot(q)], p + m.sd.off_x);
+      } else {
+        buf[pslot(q)] = make_float4(*reinterpret_cast<const float *>(p + m.sd.off_x), *reinterpret_cast<const float *>(p + m.sd.off_y),
+                                    *reinterpret_cast<const float *>(p + m.sd.off_z), 1.0f);
+      }
+    }
+  }
+}
+
 template<int PT, int TMAX, int MINB>
 __global__ void __launch_bounds__(TMAX, MINB)
-k_extract_rings2(const RingArgs a)
+k_extract_rings(const RingArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const DevParams & prm = a.prm;
+  constexpr int PM = PT > 0 ? PT : MAX_PADDING;
   const int P = PT > 0 ? PT : prm.P;
   const int B = prm.B;
-  const RingSmem2 s = carve2(smem_raw, a.cap, prm.P);
+  const RingSmem s = carve_ring(smem_raw, a.cap, prm.P);
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
   const int NW = s.nwords;
   const int data_words = a.cap / 32;
-  auto arr = [&](int k) -> uint32_t * { return s.bits + (size_t)k * NW; };
-  auto arr_bytes = [&](int k) -> uint8_t * { return reinterpret_cast<uint8_t *>(s.bits + (size_t)k * NW) + 4; };
+  const int word_threads = (data_words + 31) & ~31;
+  auto arr = [&](int k) -> uint32_t * { return s.bits + k * NW; };
+  auto arr_bytes = [&](int k) -> uint8_t * { return reinterpret_cast<uint8_t *>(s.bits + k * NW) + 4; };
+
+  const uint32_t n_work = a.counters[C_N_WORK];
+  const uint32_t G = gridDim.x;
+  uint32_t w = blockIdx.x;
+  if (w >= n_work) { return; }
 
   // pad words are zero for the whole kernel; data words are rewritten for every ring
-  for (int i = tid; i < ring2_arrays(prm.P) * NW; i += T) { s.bits[i] = 0; }
+  for (int i = tid; i < ring_arrays(prm.P) * NW; i += T) { s.bits[i] = 0; }
+  // ---- prologue: descriptors of rings 0, 1 (and the item of ring 2), data of ring 0
+  if (tid == 0) {
+    s.items[0] = a.work[w];
+    if (w + G < n_work) { s.items[1] = a.work[w + G]; }
+    if (w + 2 * G < n_work) { s.items[2] = a.work[w + 2 * G]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    prefetch_meta(a, s, 0);
+    if (w + G < n_work) { prefetch_meta(a, s, 1); }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+  issue_ring_loads(a, s.meta[0], s.pts[0], tid, T);
 
-  for (;;) {
+  for (uint32_t it = 0; w < n_work; it++, w += G) {
+    // ---- top of ring `it`: its xyz (issued one ring ago) and the descriptors of ring it+1 have landed
+    if (tid < 16) { s.misc[tid] = (tid == N_POS_NONASC || tid == N_POS_ASC) ? -1 : 0; }
+    for (int k = tid; k < data_words; k += T) { arr(A_SB)[1 + k] = 0; }
+    cp_async_wait_all();
     __syncthreads();
-    if (tid == 0) { s.misc[N_WORK] = (int)atomicAdd(&a.counters[C_WORK_NEXT], 1u); }
-    if (tid >= 1 && tid < 16) { s.misc[tid] = tid == N_POS_NONASC || tid == N_POS_ASC ? -1 : 0; }
-    for (int w = tid; w < data_words; w += T) { arr(A_SB)[1 + w] = 0; }
-    __syncthreads();
-    const uint32_t wi = (uint32_t)s.misc[N_WORK];
-    if (wi >= a.counters[C_N_WORK]) { break; }
-    const uint2 item = a.work[wi];
-    const ScanDesc sd = a.scans[item.x];
+    // descriptors two rings ahead, item three rings ahead, xyz one ring ahead
+    if (tid == 0) {
+      if (w + 3 * (uint64_t)G < n_work) { cp_async8(&s.items[(it + 3) & 3], &a.work[w + 3 * G]); }
+      if (w + 2 * (uint64_t)G < n_work) { prefetch_meta(a, s, it + 2); }
+    }
+    if (w + G < n_work) { issue_ring_loads(a, s.meta[(it + 1) % 3], s.pts[(it + 1) & 1], tid, T); }
+
+    const RingMeta & meta = s.meta[it % 3];
+    float4 * pts = s.pts[it & 1];
+    const uint2 item = s.items[it & 3];
     lfx_ring_info * ring_info = &a.rings[(size_t)item.x * a.max_rings + item.y];
-    const int n = (int)ring_info->count;
-    const uint64_t pos0 = sd.point_base + ring_info->offset;
-    const uint32_t status_in = ring_info->status;
+    const int n = (int)meta.info.count;
+    const uint64_t pos0 = meta.sd.point_base + meta.info.offset;
+    const uint32_t status_in = meta.info.status;
 
     // ---- rings that contribute nothing: sparse (ring.cpp:46-59) or over capacity
     if (status_in != LFX_RING_OK) {
       for (int i = tid; i < n; i += T) {
         a.labels[pos0 + i] = LFX_LABEL_NONE;
-        if (a.sorted_src) { a.sorted_src[pos0 + i] = a.idx[pos0 + i]; }
+        if (a.sorted_src) { a.sorted_src[pos0 + i] = src_index(a, meta, pos0, i); }
         if (a.curvature) { a.curvature[pos0 + i] = 0.0; }
       }
       if (status_in == LFX_RING_TOO_LONG && tid == 0) {
         if (atomicExch(&a.counters[C_ERR_FLAG], LFX_E_CAPACITY) == 0) { a.counters[C_ERR_SCAN] = item.x; a.counters[C_ERR_RING] = item.y; }
       }
+      __syncthreads();
       continue;
     }
 
-    // ---- phase 0: coalesced gather of the ring into shared memory (bucket order = source order)
+    // ---- phase 1: polar-angle order (SortByAtan2, ring.hpp:101-112). One exact comparator evaluation per
+    //      cyclic neighbour pair decides whether the ring already is a rotated ascending (n-1 ascents) or
+    //      rotated descending (<= 1 ascent) sequence. For sources addressed by (first, stride) the ring
+    //      field of every point is checked here as well (the lines were just fetched: L2 hits).
     {
-      float rx[PTS], ry[PTS];
+      int cnt = 0, pos_na = -1, pos_a = -1, bad_ring = 0;
+      uint32_t rid[PTS];
+      if (meta.src.y) {
 #pragma unroll
-      for (int m = 0; m < PTS; m++) {
-        const int q = tid + m * T;
-        rx[m] = 0.f; ry[m] = 0.f;
-        if (q < n) {
-          const uint32_t src = a.idx[pos0 + q];
-          const uint8_t * p = sd.data + (size_t)src * sd.point_step;
-          float x, y, z;
-          if (sd.vec_ok) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(p + sd.off_x));
-            x = v.x; y = v.y; z = v.z;
-          } else {
-            x = *reinterpret_cast<const float *>(p + sd.off_x);
-            y = *reinterpret_cast<const float *>(p + sd.off_y);
-            z = *reinterpret_cast<const float *>(p + sd.off_z);
+        for (int m = 0; m < PTS; m++) {
+          const int q = tid + m * T;
+          rid[m] = item.y;
+          if (q < n) {
+            rid[m] = load_ring_id(meta.sd.data + (size_t)(meta.src.x + (uint32_t)q * meta.src.y) * meta.sd.point_step + meta.sd.off_ring, meta.sd.ring_dt);
           }
-          const int sl = fslot(q);
-          s.fx[sl] = x; s.fy[sl] = y; s.fz[sl] = z;
-          rx[m] = x; ry[m] = y;
         }
       }
-      __syncthreads();
-
-      // ---- phase 1: polar-angle order (SortByAtan2, ring.hpp:101-112). One exact comparator
-      //      evaluation per cyclic neighbour pair decides whether the ring already is a rotated
-      //      ascending (n-1 ascents) or rotated descending (<= 1 ascent) sequence.
-      int cnt = 0, pos_na = -1, pos_a = -1;
       if (a.force_order_path == 0) {
 #pragma unroll
         for (int m = 0; m < PTS; m++) {
           const int q = tid + m * T;
           if (q < n) {
             const int q1 = q + 1 == n ? 0 : q + 1;
-            const bool asc = polar_less(rx[m], ry[m], s.fx[fslot(q1)], s.fy[fslot(q1)]);
+            const float4 pa = pts[pslot(q)], pb = pts[pslot(q1)];
+            const bool asc = polar_less(pa.x, pa.y, pb.x, pb.y);
             cnt += asc ? 1 : 0;
             if (asc) { pos_a = q; } else { pos_na = q; }   // q grows with m: keeps the largest
           }
         }
+      }
+      if (meta.src.y) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-          pos_na = max(pos_na, __shfl_xor_sync(0xFFFFFFFFu, pos_na, o));
-          pos_a = max(pos_a, __shfl_xor_sync(0xFFFFFFFFu, pos_a, o));
-        }
-        if (lane == 0) {
-          atomicAdd(&s.misc[N_CNT_ASC], cnt);
-          atomicMax(&s.misc[N_POS_NONASC], pos_na);
-          atomicMax(&s.misc[N_POS_ASC], pos_a);
-        }
+        for (int m = 0; m < PTS; m++) { bad_ring |= rid[m] != item.y; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        pos_na = max(pos_na, __shfl_xor_sync(0xFFFFFFFFu, pos_na, o));
+        pos_a = max(pos_a, __shfl_xor_sync(0xFFFFFFFFu, pos_a, o));
+        bad_ring |= __shfl_xor_sync(0xFFFFFFFFu, bad_ring, o);
+      }
+      if (lane == 0) {
+        if (cnt) { atomicAdd(&s.misc[N_CNT_ASC], cnt); }
+        if (pos_na >= 0) { atomicMax(&s.misc[N_POS_NONASC], pos_na); }
+        if (pos_a >= 0) { atomicMax(&s.misc[N_POS_ASC], pos_a); }
+        if (bad_ring) { s.misc[N_BADRING] = 1; }
       }
       __syncthreads();
     }
+    if (s.misc[N_BADRING]) {
+      // the (first, stride) hypothesis of k_probe_layout is wrong for this scan: flag it, the general
+      // ingest pass redoes the whole scan; nothing of this ring is used
+      if (tid == 0) { atomicOr(&a.scan_flags[item.x], 1u); }
+      __syncthreads();
+      continue;
+    }
     OrderMap om;
     om.n = n;
+    om.mode = 0; om.start = 0;
     int order_path = a.force_order_path;
     if (order_path == 0) {
       const int cnt_asc = s.misc[N_CNT_ASC];
@@ -306,59 +420,52 @@ k_extract_rings2(const RingArgs a)
       if (order_path == 1) {
         uint32_t * keys = reinterpret_cast<uint32_t *>(s.dr - 32);  // aliases the (not yet written) range array
         for (int i = tid; i < n2; i += T) {
-          keys[i] = i < n ? polar_key19(s.fx[fslot(i)], s.fy[fslot(i)], i) : 0xFFFFFFFFu;
+          if (i < n) { const float4 v = pts[pslot(i)]; keys[i] = polar_key19(v.x, v.y, i); } else { keys[i] = 0xFFFFFFFFu; }
         }
         bitonic_u32(keys, n2);
         for (int i = tid; i < n; i += T) { s.perm[i] = (uint16_t)(keys[i] & 0x1FFFu); }
         __syncthreads();
         int bad = 0;  // verify with the exact comparator: no adjacent inversion
         for (int i = tid; i + 1 < n; i += T) {
-          const int p0 = fslot(s.perm[i]), p1 = fslot(s.perm[i + 1]);
-          if (polar_less(s.fx[p1], s.fy[p1], s.fx[p0], s.fy[p0])) { bad = 1; }
+          const float4 v0 = pts[pslot(s.perm[i])], v1 = pts[pslot(s.perm[i + 1])];
+          if (polar_less(v1.x, v1.y, v0.x, v0.y)) { bad = 1; }
         }
         if (__syncthreads_or(bad)) { order_path = 2; }
       }
       if (order_path == 2) {
         uint16_t * pp = reinterpret_cast<uint16_t *>(s.dr - 32);  // n2 <= 8192 entries fit the range array
         for (int i = tid; i < n2; i += T) { pp[i] = (uint16_t)i; }
-        bitonic_exact2(pp, n, n2, s.fx, s.fy);
+        bitonic_exact(pp, n, n2, pts);
         for (int i = tid; i < n; i += T) { s.perm[i] = pp[i]; }
         __syncthreads();
       }
       // physically reorder the coordinates so that the map becomes the identity
-      float gx[PTS], gy[PTS], gz[PTS];
+      float4 g[PTS];
 #pragma unroll
       for (int m = 0; m < PTS; m++) {
         const int p = tid + m * T;
-        if (p < n) { const int sl = fslot(s.perm[p]); gx[m] = s.fx[sl]; gy[m] = s.fy[sl]; gz[m] = s.fz[sl]; }
+        if (p < n) { g[m] = pts[pslot(s.perm[p])]; }
       }
       __syncthreads();
 #pragma unroll
       for (int m = 0; m < PTS; m++) {
         const int p = tid + m * T;
-        if (p < n) { const int sl = fslot(p); s.fx[sl] = gx[m]; s.fy[sl] = gy[m]; s.fz[sl] = gz[m]; }
+        if (p < n) { pts[pslot(p)] = g[m]; }
       }
-      om.mode = 0; om.start = 0;
       __syncthreads();
     }
 
     // ---- ring-level preconditions (the reference throws std::invalid_argument, feature_extraction.cpp:154-156)
     bool skip = (n < 2 * P + 1) || (n - 2 * P < B);  // convolution.cpp:39-43, index_range.cpp:35-40
-    if (!skip) {
-      if (tid <= B) {  // IndexRange::Boundary index_range.cpp:60-66, evaluated without contraction
-        const double sdb = (double)P, edb = (double)(n - P), nb = (double)B, j = (double)tid;
-        const double t1 = __dmul_rn(sdb, __dsub_rn(1.0, __ddiv_rn(j, nb)));
-        const double t2 = __ddiv_rn(__dmul_rn(edb, j), nb);
-        s.bnd[tid] = (int)__dadd_rn(t1, t2);
+    if (!skip && tid <= B) {  // IndexRange::Boundary index_range.cpp:60-66, evaluated without contraction
+      const double sdb = (double)P, edb = (double)(n - P), nb = (double)B, j = (double)tid;
+      const double t1 = __dmul_rn(sdb, __dsub_rn(1.0, __ddiv_rn(j, nb)));
+      const double t2 = __ddiv_rn(__dmul_rn(edb, j), nb);
+      const int b1 = (int)__dadd_rn(t1, t2);
+      s.bnd[tid] = b1;
+      if (tid >= 1) {  // b1 - 1 is the last position of sector tid - 1
+        atomicOr(&arr(A_SB)[1 + ((b1 - 1) >> 5)], 1u << ((b1 - 1) & 31));
       }
-      __syncthreads();
-      int bad = 0;
-      if (tid < B) {
-        if (s.bnd[tid + 1] - s.bnd[tid] < 2) { bad = 1; }  // Slice -> NeighborCheckXY ctor, neighbor.hpp:71-75
-        const int last = s.bnd[tid + 1] - 1;                // last position of sector tid
-        if (last >= 0) { atomicOr(&arr(A_SB)[1 + (last >> 5)], 1u << (last & 31)); }
-      }
-      skip = __syncthreads_or(bad) != 0;
     }
 
     const int p0 = PTS * tid;
@@ -370,7 +477,7 @@ k_extract_rings2(const RingArgs a)
       for (int k = 0; k <= PTS; k++) {
         const int p = p0 + k;
         xk[k] = 0.f; yk[k] = 0.f;
-        if (p < n) { const int sl = fslot(om.at(p)); xk[k] = s.fx[sl]; yk[k] = s.fy[sl]; }
+        if (p < n) { const float2 v = *reinterpret_cast<const float2 *>(&pts[pslot(om.at(p))]); xk[k] = v.x; yk[k] = v.y; }
       }
 #pragma unroll
       for (int k = 0; k < PTS; k++) {
@@ -380,11 +487,15 @@ k_extract_rings2(const RingArgs a)
       }
     }
     __syncthreads();
+    if (!skip) {
+      int bad = 0;
+      if (tid < B && s.bnd[tid + 1] - s.bnd[tid] < 2) { bad = 1; }  // Slice -> NeighborCheckXY ctor, neighbor.hpp:71-75
+      if (bad) { s.misc[N_SKIP] = 1; }
+    }
 
     // ---- phase 3: per-point predicates as bytes of bit streams, curvature in a register window
     if (!skip) {
-      constexpr int PM = PT > 0 ? PT : MAX_PADDING;
-      // XY range of positions p0 - P .. p0 + 8 + 2P - 1  (index j + P)
+      // XY range of positions p0 - P .. p0 + 8 + 2P - 1  (index j + PM)
       double rw[PTS + 3 * PM];
 #pragma unroll
       for (int j = -PM; j < PTS + 2 * PM; j++) {
@@ -465,29 +576,31 @@ k_extract_rings2(const RingArgs a)
     if (skip) {
       for (int i = tid; i < n; i += T) {
         a.labels[pos0 + i] = LFX_LABEL_NONE;
-        if (a.sorted_src) { a.sorted_src[pos0 + i] = a.idx[pos0 + (order_path >= 1 ? (int)s.perm[i] : om.at(i))]; }
+        if (a.sorted_src) { a.sorted_src[pos0 + i] = src_index(a, meta, pos0, order_path >= 1 ? (int)s.perm[i] : om.at(i)); }
         if (a.curvature) { a.curvature[pos0 + i] = 0.0; }
       }
-      if (tid == 0) { ring_info->status = LFX_RING_SKIPPED; ring_info->order_path = order_path; }
+      if (tid == 0) { ring_info->status = LFX_RING_SKIPPED; ring_info->order_path = order_path; ring_info->n_edge = 0; ring_info->n_surface = 0; }
+      __syncthreads();
       continue;
     }
 
-    // ---- phase 4: bit-sliced selection, one thread per 32-position word.
+    // ---- phase 4: bit-sliced selection, one thread per 32-position word (first `word_threads` threads,
+    //      synchronised on their own hardware barrier).
     //      The greedy walk of label.hpp:85-94 / 124-133 over the (value, index)-sorted order is the
     //      lexicographically-first maximal independent set of the symmetric cover relation
     //      (fill.hpp:101-117 clipped to the sector), i.e. the unique solution of
     //          x_i = cand_i && !exists j in window(i): key(j) before key(i) && x_j
     //      (dependencies are acyclic by key order), reached by chaotic iteration from x = 0.
-    {
-      constexpr int PM = PT > 0 ? PT : MAX_PADDING;
-      const int w = tid;
-      const bool active = w < data_words;
+    if (tid < word_threads) {
+      const int wd = tid;
+      const bool active = wd < data_words;
       uint32_t gp[PM], gm[PM], sp[PM], sm[PM], vp[PM], vm[PM];
       uint32_t cand_e = 0, cand_s0 = 0;
+      uint32_t * XE = arr(A_XE), * XS = arr(A_XS);
       if (active) {
         const uint32_t * LS = arr(A_LS);
-        const uint32_t lsm = LS[w], ls0 = LS[w + 1], lsp = LS[w + 2];  // words w-1, w, w+1
-        uint32_t v_prev = 0xFFFFFFFFu, v_cur = 0xFFFFFFFFu;           // V_0 = all ones
+        const uint32_t lsm = LS[wd], ls0 = LS[wd + 1], lsp = LS[wd + 2];  // words wd-1, wd, wd+1
+        uint32_t v_prev = 0xFFFFFFFFu, v_cur = 0xFFFFFFFFu;              // V_0 = all ones
 #pragma unroll
         for (int d = 1; d <= PM; d++) {
           if (d <= P) {
@@ -495,7 +608,7 @@ k_extract_rings2(const RingArgs a)
             v_cur &= d == 1 ? ls0 : shr_bits(ls0, lsp, d - 1);
             v_prev &= d == 1 ? lsm : shr_bits(lsm, ls0, d - 1);
             const uint32_t * C = arr(A_C0 + d - 1);
-            const uint32_t c_prev = C[w], c_cur = C[w + 1];
+            const uint32_t c_prev = C[wd], c_cur = C[wd + 1];
             const uint32_t a_cur = c_cur & v_cur, a_prev = c_prev & v_prev;     // key(i+d) > key(i), in window
             const uint32_t b_cur = ~c_cur & v_cur, b_prev = ~c_prev & v_prev;   // key(i+d) < key(i), in window
             gp[d - 1] = a_cur;                             // edge pass: i+d dominates i
@@ -506,30 +619,35 @@ k_extract_rings2(const RingArgs a)
             vm[d - 1] = shl_bits(v_prev, v_cur, d);
           }
         }
-        cand_e = arr(A_E)[w + 1];
-        cand_s0 = arr(A_S0)[w + 1];
+        cand_e = arr(A_E)[wd + 1];
+        cand_s0 = arr(A_S0)[wd + 1];
+        XE[wd + 1] = 0; XS[wd + 1] = 0;
       }
-      uint32_t * XE = arr(A_XE), * XS = arr(A_XS);
-      if (active) { XE[w + 1] = 0; XS[w + 1] = 0; }
-      __syncthreads();
+      bar1_or(0, word_threads);
       // edge pass
       for (;;) {
         int changed = 0;
         if (active) {
-          const uint32_t xl = XE[w], xc = XE[w + 1], xr = XE[w + 2];
-          uint32_t blocked = 0;
+          const uint32_t xl = XE[wd], xr = XE[wd + 2];
+          const uint32_t x0 = XE[wd + 1];
+          uint32_t xc = x0;
+          for (int rep = 0; rep < 4; rep++) {   // a few local sweeps against frozen neighbour words
+            uint32_t blocked = 0;
 #pragma unroll
-          for (int d = 1; d <= PM; d++) {
-            if (d <= P) { blocked |= (gp[d - 1] & shr_bits(xc, xr, d)) | (gm[d - 1] & shl_bits(xl, xc, d)); }
+            for (int d = 1; d <= PM; d++) {
+              if (d <= P) { blocked |= (gp[d - 1] & shr_bits(xc, xr, d)) | (gm[d - 1] & shl_bits(xl, xc, d)); }
+            }
+            const uint32_t xn = cand_e & ~blocked;
+            if (xn == xc) { break; }
+            xc = xn;
           }
-          const uint32_t xn = cand_e & ~blocked;
-          if (xn != xc) { XE[w + 1] = xn; changed = 1; }
+          if (xc != x0) { XE[wd + 1] = xc; changed = 1; }
         }
-        if (!__syncthreads_or(changed)) { break; }
+        if (!bar1_or(changed, word_threads)) { break; }
       }
       uint32_t xe = 0, ce = 0;
       if (active) {
-        const uint32_t xl = XE[w], xc = XE[w + 1], xr = XE[w + 2];
+        const uint32_t xl = XE[wd], xc = XE[wd + 1], xr = XE[wd + 2];
         xe = xc; ce = xc;
 #pragma unroll
         for (int d = 1; d <= PM; d++) {
@@ -541,20 +659,26 @@ k_extract_rings2(const RingArgs a)
       for (;;) {
         int changed = 0;
         if (active) {
-          const uint32_t xl = XS[w], xc = XS[w + 1], xr = XS[w + 2];
-          uint32_t blocked = 0;
+          const uint32_t xl = XS[wd], xr = XS[wd + 2];
+          const uint32_t x0 = XS[wd + 1];
+          uint32_t xc = x0;
+          for (int rep = 0; rep < 4; rep++) {
+            uint32_t blocked = 0;
 #pragma unroll
-          for (int d = 1; d <= PM; d++) {
-            if (d <= P) { blocked |= (sp[d - 1] & shr_bits(xc, xr, d)) | (sm[d - 1] & shl_bits(xl, xc, d)); }
+            for (int d = 1; d <= PM; d++) {
+              if (d <= P) { blocked |= (sp[d - 1] & shr_bits(xc, xr, d)) | (sm[d - 1] & shl_bits(xl, xc, d)); }
+            }
+            const uint32_t xn = cand_s & ~blocked;
+            if (xn == xc) { break; }
+            xc = xn;
           }
-          const uint32_t xn = cand_s & ~blocked;
-          if (xn != xc) { XS[w + 1] = xn; changed = 1; }
+          if (xc != x0) { XS[wd + 1] = xc; changed = 1; }
         }
-        if (!__syncthreads_or(changed)) { break; }
+        if (!bar1_or(changed, word_threads)) { break; }
       }
       // ---- phase 5: covers, occlusion fills, label priority - all per word
       if (active) {
-        const uint32_t xl = XS[w], xc = XS[w + 1], xr = XS[w + 2];
+        const uint32_t xl = XS[wd], xc = XS[wd + 1], xr = XS[wd + 2];
         uint32_t cs = xc;
 #pragma unroll
         for (int d = 1; d <= PM; d++) {
@@ -562,8 +686,8 @@ k_extract_rings2(const RingArgs a)
         }
         // occlusion (occlusion.hpp:37-91): a trigger within P+1 positions whose chain of links reaches i
         const uint32_t * LK = arr(A_LINK), * TL = arr(A_TL), * TRS = arr(A_TRS);
-        const uint32_t lkm = LK[w], lk0 = LK[w + 1], lkp = LK[w + 2];
-        const uint32_t tlm = TL[w], tl0 = TL[w + 1], tr0 = TRS[w + 1], trp = TRS[w + 2];
+        const uint32_t lkm = LK[wd], lk0 = LK[wd + 1], lkp = LK[wd + 2];
+        const uint32_t tlm = TL[wd], tl0 = TL[wd + 1], tr0 = TRS[wd + 1], trp = TRS[wd + 2];
         uint32_t occ = 0, ch = 0xFFFFFFFFu, chr = 0xFFFFFFFFu;
 #pragma unroll
         for (int m = 0; m <= PM; m++) {
@@ -575,21 +699,21 @@ k_extract_rings2(const RingArgs a)
           }
         }
         // final label = ParallelBeam > OutOfRange > Occluded > selection (feature_extraction.cpp:133-138)
-        const uint32_t pb = arr(A_PB)[w + 1], oor = arr(A_OOR)[w + 1];
+        const uint32_t pb = arr(A_PB)[wd + 1], oor = arr(A_OOR)[wd + 1];
         const uint32_t m7 = pb, m5 = oor & ~pb, m6 = occ & ~oor & ~pb, rest = ~(pb | oor | occ);
         const uint32_t m1 = xe & rest, m3 = xc & ~xe & rest, m4 = cs & ~xc & ~xe & rest, m2 = ce & ~xe & ~cs & rest;
-        arr(A_L0)[w + 1] = m7 | m5 | m1 | m3;
-        arr(A_L1)[w + 1] = m7 | m6 | m3 | m2;
-        arr(A_L2)[w + 1] = m7 | m5 | m6 | m4;
-        arr(A_EM)[w + 1] = m1;
-        arr(A_SM)[w + 1] = m3;
-        s.wpre[w] = __popc(m1);
-        s.wpre[NW + w] = __popc(m3);
+        arr(A_L0)[wd + 1] = m7 | m5 | m1 | m3;
+        arr(A_L1)[wd + 1] = m7 | m6 | m3 | m2;
+        arr(A_L2)[wd + 1] = m7 | m5 | m6 | m4;
+        arr(A_EM)[wd + 1] = m1;
+        arr(A_SM)[wd + 1] = m3;
+        s.wpre[wd] = __popc(m1);
+        s.wpre[NW + wd] = __popc(m3);
       }
-      __syncthreads();
-      // exclusive prefix of the per-word counts: warp 0 for Edge, warp 1 for Surface
-      if (tid < 64) {
-        uint32_t * c = s.wpre + (tid >> 5) * NW;
+      bar1_or(0, word_threads);
+      // exclusive prefix of the per-word counts: warp 0 for Edge, warp 1 (or warp 0 again) for Surface
+      for (int which = tid >> 5; which < 2; which += word_threads >> 5) {
+        uint32_t * c = s.wpre + which * NW;
         const int per = (data_words + 31) / 32;
         const int b0 = lane * per;
         uint32_t sum = 0;
@@ -599,10 +723,10 @@ k_extract_rings2(const RingArgs a)
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) { inc += v; } }
         uint32_t run = inc - sum;
         for (int k = 0; k < per; k++) { if (b0 + k < data_words) { const uint32_t v = c[b0 + k]; c[b0 + k] = run; run += v; } }
-        if (lane == 31) { if (tid < 32) { ring_info->n_edge = inc; } else { ring_info->n_surface = inc; } }
+        if (lane == 31) { if (which == 0) { ring_info->n_edge = inc; } else { ring_info->n_surface = inc; } }
       }
-      __syncthreads();
     }
+    __syncthreads();
 
     // ---- phase 6: outputs. Label bytes (8 per thread), feature points staged (edge ascending from the
     //      ring start, surface descending from the ring end).
@@ -619,28 +743,30 @@ k_extract_rings2(const RingArgs a)
 #pragma unroll
         for (int k = 0; k < PTS; k++) { if (p0 + k < n) { dst[k] = (uint8_t)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xFFu); } }
       }
-      const int w = tid >> 2, sh = (tid & 3) * 8;
+      const int wq = tid >> 2, sh = (tid & 3) * 8;
       uint32_t em = arr_bytes(A_EM)[tid], smk = arr_bytes(A_SM)[tid];
       if (em | smk) {
-        uint32_t re = s.wpre[w] + __popc(arr(A_EM)[w + 1] & ((1u << sh) - 1u));
-        uint32_t rs = s.wpre[NW + w] + __popc(arr(A_SM)[w + 1] & ((1u << sh) - 1u));
+        uint32_t re = s.wpre[wq] + __popc(arr(A_EM)[wq + 1] & ((1u << sh) - 1u));
+        uint32_t rs = s.wpre[NW + wq] + __popc(arr(A_SM)[wq + 1] & ((1u << sh) - 1u));
         while (em) {
           const int k = __ffs(em) - 1; em &= em - 1;
-          const int sl = fslot(om.at(p0 + k));
-          a.stage[pos0 + re++] = make_float4(s.fx[sl], s.fy[sl], s.fz[sl], 1.0f);
+          float4 v = pts[pslot(om.at(p0 + k))]; v.w = 1.0f;
+          a.stage[pos0 + re++] = v;
         }
         while (smk) {
           const int k = __ffs(smk) - 1; smk &= smk - 1;
-          const int sl = fslot(om.at(p0 + k));
-          a.stage[pos0 + (uint32_t)(n - 1) - rs++] = make_float4(s.fx[sl], s.fy[sl], s.fz[sl], 1.0f);
+          float4 v = pts[pslot(om.at(p0 + k))]; v.w = 1.0f;
+          a.stage[pos0 + (uint32_t)(n - 1) - rs++] = v;
         }
       }
     }
     if (a.sorted_src) {
-      for (int i = tid; i < n; i += T) { a.sorted_src[pos0 + i] = a.idx[pos0 + (order_path >= 1 ? (int)s.perm[i] : om.at(i))]; }
+      for (int i = tid; i < n; i += T) { a.sorted_src[pos0 + i] = src_index(a, meta, pos0, order_path >= 1 ? (int)s.perm[i] : om.at(i)); }
     }
     if (tid == 0) { ring_info->order_path = order_path; }
+    __syncthreads();
   }
+  cp_async_wait_all();
 }
 
 }  // namespace lfxk
