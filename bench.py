@@ -270,7 +270,7 @@ def main():
     ms_per_step = ms_total / args.steps
     value = n_points * world / (ms_per_step * 1e-3)
 
-    # ---- dominant kernel (k_extract_rings) timed live with CUDA events on the launching stream
+    # ---- dominant kernel (k_extract_sectors) timed live with CUDA events on the launching stream
     counts, offsets = np.zeros((scans_per_gpu, 2), np.uint32), np.zeros((scans_per_gpu + 1, 2), np.uint32)
     lib.lfx_fetch_counts(fe.handle, counts.ctypes.data, offsets.ctypes.data)
     n_feat = int(offsets[-1, 0]) + int(offsets[-1, 1])
@@ -283,7 +283,7 @@ def main():
         stage.append(fe.last_stage_ms())
     fe.set_stage_timing(False)
     stage = np.array(stage[1:]) if len(stage) > 1 else np.array(stage)
-    ring_ms = float(stage[:, 1].mean())
+    ring_ms = float(stage[:, 1].mean())  # k_extract_sectors (all K classes; one of them holds the whole batch)
     peaks, peak_kind = measured_peaks()
     peak = float(peaks["hbm_gbs"])
     achieved = alg_bytes / (ring_ms * 1e-3) / 1e9
@@ -294,10 +294,11 @@ def main():
         traffic = float(tj["dram_bytes_per_point"][sensor]) * n_points
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_extract_rings", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_extract_sectors", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
                 "kernel_ms": ring_ms, "algorithmic_bytes": alg_bytes,
-                "stage_ms": {"ingest": float(stage[:, 0].mean()), "rings": ring_ms, "pack": float(stage[:, 2].mean())},
+                "stage_ms": {"probe": float(stage[:, 0].mean()), "sectors": ring_ms, "general": float(stage[:, 2].mean()),
+                             "pack": float(stage[:, 3].mean())},
                 "pipeline_frac": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
 
     # ---- e2e: same metric through the public C ABI with pinned HOST buffers

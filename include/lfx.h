@@ -213,9 +213,22 @@ int lfx_memcpy_d2h(lfx_handle *h, void *dst_host, const void *src_device, size_t
 /* Kernels launched / graph launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t lfx_kernel_launch_count(const lfx_handle *h);
 /* Device time of the last batch's stages, measured with CUDA events on the handle's stream:
- * ms[0]=ingest(hist+plan+scatter) ms[1]=ring kernel ms[2]=pack. Only when timing was enabled. */
+ * ms[0]=layout probe, ms[1]=sector kernel (fast path), ms[2]=general path (list + hist + plan +
+ * scatter + ring kernel), ms[3]=pack. Only when timing was enabled. */
 int lfx_set_stage_timing(lfx_handle *h, int enabled);
-int lfx_last_stage_ms(lfx_handle *h, float *ms3);
+int lfx_last_stage_ms(lfx_handle *h, float *ms4);
+
+/* Which path the scans of the last batch took (synchronises). A scan is "regular" when its points are
+ * in sensor firing order with a fixed ring period and every ring is a rotated monotone sequence of polar
+ * angles; regular scans run on the sector kernel, everything else (and every scan that fails one of the
+ * sector kernel's checks) on the general bucket + sort + ring kernel. Results are identical. */
+typedef struct lfx_batch_stats {
+  uint32_t fast_rings[3];   /* rings handed to the sector kernel, per positions-per-lane class (10, 11, 12) */
+  uint32_t general_scans;   /* scans that took the general path */
+  uint32_t general_rings;   /* rings processed by the general ring kernel */
+  uint32_t reserved[3];
+} lfx_batch_stats;
+int lfx_last_batch_stats(lfx_handle *h, lfx_batch_stats *out);
 
 /* ------------------------------------------------------------------ synthetic scans
  * Deterministic generator for the BASELINE.json sensor shapes (test/bench input, not part of the

@@ -109,6 +109,11 @@ class ScanOutput(C.Structure):
     ]
 
 
+class BatchStats(C.Structure):
+    _fields_ = [("fast_rings", C.c_uint32 * 3), ("general_scans", C.c_uint32), ("general_rings", C.c_uint32),
+                ("reserved", C.c_uint32 * 3)]
+
+
 class SynthSpec(C.Structure):
     _fields_ = [
         ("n_rings", C.c_int),
@@ -185,6 +190,7 @@ def lib() -> C.CDLL:
     L.lfx_kernel_launch_count.restype = C.c_uint64
     L.lfx_set_stage_timing.argtypes = [H, C.c_int]
     L.lfx_last_stage_ms.argtypes = [H, C.c_void_p]
+    L.lfx_last_batch_stats.argtypes = [H, C.POINTER(BatchStats)]
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]
     L.lfx_synth_scan_host.argtypes = [C.POINTER(SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
     L.lfx_synth_batch_device.argtypes = [H, C.POINTER(SynthSpec), C.c_uint64, C.c_int, C.c_void_p]

@@ -20,6 +20,7 @@
 #include "lfx.h"
 #include "lfx_kernels.cuh"
 #include "lfx_ring.cuh"
+#include "lfx_sector.cuh"
 #include "lfx_synth.h"
 
 using namespace lfxk;
@@ -57,6 +58,10 @@ struct lfx_handle
   int cap = 0;
   int ring_threads = 0;
   void (*ring_kernel)(const RingArgs) = nullptr;
+  void (*sector_kernel[N_FAST_K])(const SectorArgs) = {nullptr, nullptr, nullptr};  // null: no fast path for these parameters
+  int sector_grid = 0, ingest_grid = 0;
+  size_t sector_smem[N_FAST_K] = {0, 0, 0};
+  bool fast_enabled = false;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -72,6 +77,9 @@ struct lfx_handle
   DevBuf<uint2> d_ring_featoff;
   DevBuf<uint2> d_ring_src;
   DevBuf<uint32_t> d_scan_flags;
+  DevBuf<uint32_t> d_gen_scan, d_gen_tile_base;
+  DevBuf<FastRing> d_fast[N_FAST_K];
+  DevBuf<SectorRec> d_rec[N_FAST_K];
   DevBuf<uint32_t> d_idx;
   DevBuf<uint8_t> d_labels;
   DevBuf<uint32_t> d_sorted_src;
@@ -101,7 +109,7 @@ struct lfx_handle
   bool have_batch = false;
 
   bool timing = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have_timing = false;
 };
 
@@ -191,6 +199,23 @@ void (*pick_ring_kernel(int padding, int threads, int * tmax))(const RingArgs)
   return pick_ring_kernel_t<0>(threads, tmax);                         // any other padding: runtime loops
 }
 
+template<int P, bool DIAG>
+void pick_sector_kernels_t(void (**out)(const SectorArgs))
+{
+  out[0] = k_extract_sectors<P, fast_k(0), DIAG, SEC_WARPS>;
+  out[1] = k_extract_sectors<P, fast_k(1), DIAG, SEC_WARPS>;
+  out[2] = k_extract_sectors<P, fast_k(2), DIAG, SEC_WARPS>;
+}
+
+// The sector kernel is compiled for the two deployed paddings (compiled default 5, launch YAML 2);
+// any other padding runs on the general ring kernel only.
+bool pick_sector_kernels(int padding, bool diag, void (**out)(const SectorArgs))
+{
+  if (padding == 5) { if (diag) { pick_sector_kernels_t<5, true>(out); } else { pick_sector_kernels_t<5, false>(out); } return true; }
+  if (padding == 2) { if (diag) { pick_sector_kernels_t<2, true>(out); } else { pick_sector_kernels_t<2, false>(out); } return true; }
+  return false;
+}
+
 int validate_params(const lfx_params & p, std::string & why)
 {
   // hyper_parameter.hpp:45-53: everything strictly positive
@@ -211,17 +236,47 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   const int max_rings = h->opt.max_rings;
   LFX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * C_COUNT, h->stream));
   if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[0], h->stream)); }
-  if (n_tiles > 0) {
-    k_ring_hist<<<n_tiles, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
-      h->d_scans.p, n_scans, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
-  }
-  k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
-    h->d_scans.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, h->d_work.p, h->d_counters, max_rings, h->params.padding, h->cap);
-  if (n_tiles > 0) {
-    k_ring_scatter<<<n_tiles, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
-      h->d_scans.p, n_scans, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
-  }
+  // ---- fast path: layout probe, then one warp per ring-sector
+  ProbeArgs pa;
+  pa.scans = h->d_scans.p;
+  pa.rings = h->d_rings.p;
+  pa.scan_flags = h->d_scan_flags.p;
+  for (int c = 0; c < N_FAST_K; c++) { pa.fast[c] = h->d_fast[c].p; }
+  pa.counters = h->d_counters;
+  pa.max_rings = max_rings;
+  pa.P = h->params.padding;
+  pa.B = h->params.n_blocks;
+  pa.enabled = h->fast_enabled ? 1 : 0;
+  k_probe_layout<<<n_scans, PROBE_THREADS, sizeof(uint32_t) * (3 * max_rings + 1), h->stream>>>(pa);
   if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[1], h->stream)); }
+  if (h->fast_enabled) {
+    for (int c = 0; c < N_FAST_K; c++) {
+      SectorArgs sa;
+      sa.fast = h->d_fast[c].p;
+      sa.n_entries = h->d_counters + C_N_FAST0 + c;
+      sa.rec = h->d_rec[c].p;
+      sa.rings = h->d_rings.p;
+      sa.scan_flags = h->d_scan_flags.p;
+      sa.labels = h->d_labels.p;
+      sa.sorted_src = h->opt.want_sorted_src ? h->d_sorted_src.p : nullptr;
+      sa.curvature = h->opt.want_curvature ? h->d_curv.p : nullptr;
+      sa.stage = h->d_stage.p;
+      sa.max_rings = max_rings;
+      sa.prm = h->dev;
+      h->sector_kernel[c]<<<h->sector_grid, SEC_WARPS * 32, h->sector_smem[c], h->stream>>>(sa);
+    }
+  }
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
+  // ---- general path for the scans flagged by the probe or by a failed check of the sector kernel
+  k_general_list<<<1, 1024, 0, h->stream>>>(h->d_scans.p, n_scans, h->d_scan_flags.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_counters);
+  const int ingest_grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_tiles, 1u), (uint32_t)h->ingest_grid);
+  k_ring_hist<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
+    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
+  k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
+    h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, h->d_work.p, h->d_counters, max_rings,
+    h->params.padding, h->cap);
+  k_ring_scatter<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
+    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
   RingArgs ra;
   ra.scans = h->d_scans.p;
   ra.idx = h->d_idx.p;
@@ -239,18 +294,33 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   ra.force_order_path = h->opt.force_order_path;
   ra.prm = h->dev;
   h->ring_kernel<<<h->ring_grid, h->ring_threads, h->ring_smem, h->stream>>>(ra);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[3], h->stream)); }
+  // ---- packing
   k_feat_offsets_a<<<n_scans, 128, 0, h->stream>>>(h->d_rings.p, h->d_ring_featoff.p, h->d_counts.p, max_rings);
   k_feat_offsets_b<<<1, 1024, 0, h->stream>>>(h->d_counts.p, h->d_offsets.p, n_scans);
+  if (h->fast_enabled) {
+    PackFastArgs pf;
+    for (int c = 0; c < N_FAST_K; c++) { pf.fast[c] = h->d_fast[c].p; pf.rec[c] = h->d_rec[c].p; }
+    pf.counters = h->d_counters;
+    pf.scan_flags = h->d_scan_flags.p;
+    pf.ring_featoff = h->d_ring_featoff.p;
+    pf.offsets = h->d_offsets.p;
+    pf.stage = h->d_stage.p;
+    pf.edge = h->d_edge.p;
+    pf.surface = h->d_surface.p;
+    pf.max_rings = max_rings;
+    pf.B = h->params.n_blocks;
+    k_pack_fast<<<h->pack_grid, 256, 0, h->stream>>>(pf);
+  }
   k_pack_copy<<<h->pack_grid, 256, 0, h->stream>>>(
     h->d_work.p, h->d_counters, h->d_scans.p, h->d_rings.p, h->d_ring_featoff.p, h->d_offsets.p, h->d_stage.p,
     h->d_edge.p, h->d_surface.p, max_rings);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[3], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[4], h->stream)); }
   LFX_CUDA(h, cudaGetLastError());
   return LFX_OK;
 }
 
-constexpr int KERNELS_PER_BATCH = 7;
+int kernels_per_batch(const lfx_handle * h) { return h->fast_enabled ? 10 + N_FAST_K + 1 : 10; }
 
 }  // namespace
 
@@ -367,6 +437,26 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->ring_grid = h->num_sms * std::max(occ, 1);
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_copy, 256, 0)) != cudaSuccess) { return bail(e, "occupancy(pack)"); }
   h->pack_grid = h->num_sms * std::max(occ, 1);
+  h->ingest_grid = h->num_sms * 8;
+  // fast path: compiled for the deployed paddings; the sort-path test knob forces the general kernel
+  h->fast_enabled = h->opt.force_order_path == 0 && params->n_blocks <= FAST_MAX_BLOCKS &&
+                    pick_sector_kernels(params->padding, h->opt.want_sorted_src || h->opt.want_curvature, h->sector_kernel);
+  if (h->fast_enabled) {
+    h->sector_smem[0] = sector_smem_bytes<fast_k(0)>(SEC_WARPS);
+    h->sector_smem[1] = sector_smem_bytes<fast_k(1)>(SEC_WARPS);
+    h->sector_smem[2] = sector_smem_bytes<fast_k(2)>(SEC_WARPS);
+    int socc = 0;
+    for (int c = 0; c < N_FAST_K; c++) {
+      if ((e = cudaFuncSetAttribute(h->sector_kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sector_smem[c])) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(sectors)"); }
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], SEC_WARPS * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
+      socc = std::max(socc, occ);
+    }
+    h->sector_grid = h->num_sms * std::max(socc, 1);
+  }
+  const size_t probe_smem = sizeof(uint32_t) * (3 * (size_t)h->opt.max_rings + 1);
+  if (probe_smem > 48 * 1024) {
+    if ((e = cudaFuncSetAttribute(k_probe_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(probe)"); }
+  }
 
   if ((e = cudaMalloc(reinterpret_cast<void **>(&h->d_counters), sizeof(uint32_t) * C_COUNT)) != cudaSuccess) { return bail(e, "cudaMalloc(counters)"); }
   if ((e = cudaMallocHost(reinterpret_cast<void **>(&h->h_counters), sizeof(uint32_t) * C_COUNT)) != cudaSuccess) { return bail(e, "cudaMallocHost(counters)"); }
@@ -387,7 +477,8 @@ void lfx_destroy(lfx_handle * h)
   cudaFree(h->d_rings.p); cudaFree(h->d_work.p); cudaFree(h->d_ring_featoff.p); cudaFree(h->d_ring_src.p); cudaFree(h->d_scan_flags.p); cudaFree(h->d_idx.p);
   cudaFree(h->d_labels.p); cudaFree(h->d_sorted_src.p); cudaFree(h->d_curv.p); cudaFree(h->d_stage.p);
   cudaFree(h->d_edge.p); cudaFree(h->d_surface.p); cudaFree(h->d_counts.p); cudaFree(h->d_offsets.p);
-  cudaFree(h->d_input.p); cudaFree(h->d_counters);
+  cudaFree(h->d_input.p); cudaFree(h->d_counters); cudaFree(h->d_gen_scan.p); cudaFree(h->d_gen_tile_base.p);
+  for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
   cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
   for (auto & ev : h->ev) { if (ev) { cudaEventDestroy(ev); } }
@@ -452,6 +543,18 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
   if ((rc = ensure(h, h->d_ring_featoff, ns * mr, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_ring_src, ns * mr, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_scan_flags, ns, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_gen_scan, ns, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_gen_tile_base, ns + 1, &regrown))) { return rc; }
+  if (h->fast_enabled) {
+    // a regular scan contributes at most min(n_points / FAST_MIN_RING, max_rings) rings to one list
+    size_t fast_cap = 0;
+    for (int s = 0; s < n_scans; s++) { fast_cap += std::min<size_t>(scans[s].n_points / FAST_MIN_RING, mr); }
+    fast_cap = std::max<size_t>(fast_cap, 1);
+    for (int c = 0; c < N_FAST_K; c++) {
+      if ((rc = ensure(h, h->d_fast[c], fast_cap, &regrown))) { return rc; }
+      if ((rc = ensure(h, h->d_rec[c], fast_cap * h->params.n_blocks, &regrown))) { return rc; }
+    }
+  }
   if ((rc = ensure(h, h->d_idx, np, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_labels, np, &regrown))) { return rc; }
   if (h->opt.want_sorted_src && (rc = ensure(h, h->d_sorted_src, np, &regrown))) { return rc; }
@@ -552,7 +655,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
       if ((rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, h->timing))) { return rc; }
       h->have_timing = h->timing;
     }
-    h->launches += KERNELS_PER_BATCH - (total_tiles == 0 ? 2 : 0);
+    h->launches += kernels_per_batch(h);
   } else {
     LFX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * C_COUNT, h->stream));
     LFX_CUDA(h, cudaMemsetAsync(h->d_offsets.p, 0, sizeof(uint32_t) * 2, h->stream));
@@ -757,13 +860,27 @@ int lfx_set_stage_timing(lfx_handle * h, int enabled)
   return LFX_OK;
 }
 
-int lfx_last_stage_ms(lfx_handle * h, float * ms3)
+int lfx_last_stage_ms(lfx_handle * h, float * ms4)
 {
-  if (!h || !ms3) { return LFX_E_BAD_PARAM; }
+  if (!h || !ms4) { return LFX_E_BAD_PARAM; }
   if (!h->have_timing) { return fail(h, LFX_E_STATE, "stage timing was not enabled for the last batch"); }
   LFX_CUDA(h, cudaSetDevice(h->device));
-  LFX_CUDA(h, cudaEventSynchronize(h->ev[3]));
-  for (int k = 0; k < 3; k++) { LFX_CUDA(h, cudaEventElapsedTime(&ms3[k], h->ev[k], h->ev[k + 1])); }
+  LFX_CUDA(h, cudaEventSynchronize(h->ev[4]));
+  for (int k = 0; k < 4; k++) { LFX_CUDA(h, cudaEventElapsedTime(&ms4[k], h->ev[k], h->ev[k + 1])); }
+  return LFX_OK;
+}
+
+int lfx_last_batch_stats(lfx_handle * h, lfx_batch_stats * out)
+{
+  if (!h || !out) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(uint32_t) * C_COUNT, cudaMemcpyDeviceToHost, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  memset(out, 0, sizeof(*out));
+  for (int c = 0; c < N_FAST_K; c++) { out->fast_rings[c] = h->h_counters[C_N_FAST0 + c]; }
+  out->general_scans = h->h_counters[C_GEN_SCANS];
+  out->general_rings = h->h_counters[C_N_WORK];
   return LFX_OK;
 }
 

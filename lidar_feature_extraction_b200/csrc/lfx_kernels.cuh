@@ -1,6 +1,9 @@
 // lfx_kernels.cuh — sm_100a kernels of the extraction path.
 //
 // Data flow for one batch (all device resident):
+//   k_probe_layout + k_extract_sectors (lfx_sector.cuh): the fast path for regular scans; scans that are
+//                   not regular, or fail its checks, are flagged and take the general path below
+//   k_general_list  compact list of the flagged scans and their ingest tiles
 //   k_ring_hist     per 2048-point tile: ring-id histogram           (MakePointIndices, ring.hpp:114-125)
 //   k_ring_plan     per scan: stable bucket offsets, ring table, work list (+ RemoveSparseRings, ring.cpp:46-59)
 //   k_ring_scatter  per tile: stable scatter of point indices into ring buckets
@@ -28,7 +31,13 @@ constexpr int INGEST_THREADS = 256; // 8 warps, 256 consecutive points each
 constexpr int MAX_PADDING = 15;     // selection windows live in 16-bit halves
 constexpr int MAX_BLOCKS = 64;
 
-enum Counter { C_N_WORK = 0, C_WORK_NEXT = 1, C_PACK_NEXT = 2, C_ERR_FLAG = 3, C_ERR_SCAN = 4, C_ERR_RING = 5, C_COUNT = 8 };
+enum Counter {
+  C_N_WORK = 0, C_WORK_NEXT = 1, C_PACK_NEXT = 2, C_ERR_FLAG = 3, C_ERR_SCAN = 4, C_ERR_RING = 5,
+  C_GEN_SCANS = 6,   // scans taking the general path (flagged by k_probe_layout or k_extract_sectors)
+  C_GEN_TILES = 7,   // ingest tiles of those scans
+  C_N_FAST0 = 8,     // + kidx: entries of the fast-path ring lists
+  C_COUNT = 16
+};
 
 struct ScanDesc
 {
@@ -121,50 +130,96 @@ __device__ __forceinline__ uint32_t polar_key(float x, float y)
 
 // ------------------------------------------------------------------ ingest: histogram
 
-__device__ __forceinline__ int find_scan_of_tile(const ScanDesc * scans, int n_scans, uint32_t tile)
+// k-th flagged scan owning general tile t: largest k with gen_tile_base[k] <= t
+__device__ __forceinline__ int find_gen_scan(const uint32_t * gen_tile_base, int n_gen, uint32_t t)
 {
-  int lo = 0, hi = n_scans - 1;
+  int lo = 0, hi = n_gen - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (scans[mid].tile_base <= tile) { lo = mid; } else { hi = mid - 1; }
+    if (gen_tile_base[mid] <= t) { lo = mid; } else { hi = mid - 1; }
   }
   return lo;
 }
 
+// single CTA: list of flagged scans + exclusive prefix of their tile counts
+__global__ void __launch_bounds__(1024)
+k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t * __restrict__ scan_flags,
+               uint32_t * __restrict__ gen_scan, uint32_t * __restrict__ gen_tile_base, uint32_t * counters)
+{
+  __shared__ uint32_t s_c[1024], s_t[1024];
+  const int tid = threadIdx.x;
+  uint32_t carry_c = 0, carry_t = 0;
+  for (int base = 0; base < n_scans; base += 1024) {
+    const int i = base + tid;
+    uint32_t f = 0, nt = 0;
+    if (i < n_scans && scan_flags[i]) { f = 1; nt = scans[i].n_tiles; }
+    s_c[tid] = f; s_t[tid] = nt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      uint32_t vc = 0, vt = 0;
+      if (tid >= off) { vc = s_c[tid - off]; vt = s_t[tid - off]; }
+      __syncthreads();
+      s_c[tid] += vc; s_t[tid] += vt;
+      __syncthreads();
+    }
+    if (f) {
+      const uint32_t k = carry_c + s_c[tid] - 1;
+      gen_scan[k] = (uint32_t)i;
+      gen_tile_base[k] = carry_t + s_t[tid] - nt;
+    }
+    carry_c += s_c[1023]; carry_t += s_t[1023];
+    __syncthreads();
+  }
+  if (tid == 0) { gen_tile_base[carry_c] = carry_t; counters[C_GEN_SCANS] = carry_c; counters[C_GEN_TILES] = carry_t; }
+}
+
 __global__ void __launch_bounds__(INGEST_THREADS)
-k_ring_hist(const ScanDesc * __restrict__ scans, int n_scans, uint16_t * __restrict__ ring16,
+k_ring_hist(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
+            const uint32_t * __restrict__ gen_tile_base, uint16_t * __restrict__ ring16,
             uint32_t * __restrict__ tile_hist, int max_rings, uint32_t * counters)
 {
   extern __shared__ uint32_t s_hist[];
   __shared__ int s_scan;
-  const uint32_t tile = blockIdx.x;
-  if (threadIdx.x == 0) { s_scan = find_scan_of_tile(scans, n_scans, tile); }
-  for (int r = threadIdx.x; r < max_rings; r += blockDim.x) { s_hist[r] = 0; }
-  __syncthreads();
-  const ScanDesc sd = scans[s_scan];
-  const uint32_t first = (tile - sd.tile_base) * TILE;
-  for (uint32_t k = threadIdx.x; k < TILE; k += blockDim.x) {
-    const uint32_t i = first + k;
-    if (i < sd.n_points) {
-      uint32_t ring = load_ring_id(sd.data + (size_t)i * sd.point_step + sd.off_ring, sd.ring_dt);
-      if (ring >= (uint32_t)max_rings) {
-        if (atomicExch(&counters[C_ERR_FLAG], LFX_E_CAPACITY) == 0) { counters[C_ERR_SCAN] = s_scan; counters[C_ERR_RING] = ring; }
-        ring = max_rings - 1;
-      }
-      ring16[sd.point_base + i] = (uint16_t)ring;
-      atomicAdd(&s_hist[ring], 1u);
+  __shared__ uint32_t s_tile;
+  const uint32_t n_tiles = counters[C_GEN_TILES];
+  const int n_gen = (int)counters[C_GEN_SCANS];
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int k = find_gen_scan(gen_tile_base, n_gen, t);
+      s_scan = (int)gen_scan[k];
+      s_tile = scans[s_scan].tile_base + (t - gen_tile_base[k]);
     }
+    for (int r = threadIdx.x; r < max_rings; r += blockDim.x) { s_hist[r] = 0; }
+    __syncthreads();
+    const ScanDesc sd = scans[s_scan];
+    const uint32_t tile = s_tile;
+    const uint32_t first = (tile - sd.tile_base) * TILE;
+    for (uint32_t k = threadIdx.x; k < TILE; k += blockDim.x) {
+      const uint32_t i = first + k;
+      if (i < sd.n_points) {
+        uint32_t ring = load_ring_id(sd.data + (size_t)i * sd.point_step + sd.off_ring, sd.ring_dt);
+        if (ring >= (uint32_t)max_rings) {
+          if (atomicExch(&counters[C_ERR_FLAG], LFX_E_CAPACITY) == 0) { counters[C_ERR_SCAN] = s_scan; counters[C_ERR_RING] = ring; }
+          ring = max_rings - 1;
+        }
+        ring16[sd.point_base + i] = (uint16_t)ring;
+        atomicAdd(&s_hist[ring], 1u);
+      }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < max_rings; r += blockDim.x) { tile_hist[(size_t)tile * max_rings + r] = s_hist[r]; }
   }
-  __syncthreads();
-  for (int r = threadIdx.x; r < max_rings; r += blockDim.x) { tile_hist[(size_t)tile * max_rings + r] = s_hist[r]; }
 }
 
 // ------------------------------------------------------------------ ingest: plan (one CTA per scan)
 
 __global__ void __launch_bounds__(256)
-k_ring_plan(const ScanDesc * __restrict__ scans, uint32_t * __restrict__ tile_hist, lfx_ring_info * __restrict__ rings,
-            uint2 * __restrict__ ring_src, uint2 * __restrict__ work, uint32_t * counters, int max_rings, int padding, int cap)
+k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ scan_flags, uint32_t * __restrict__ tile_hist,
+            lfx_ring_info * __restrict__ rings, uint2 * __restrict__ ring_src, uint2 * __restrict__ work, uint32_t * counters,
+            int max_rings, int padding, int cap)
 {
+  if (!scan_flags[blockIdx.x]) { return; }  // handled by the fast path
   extern __shared__ uint32_t s_cnt[];  // [max_rings] counts, then [max_rings] offsets
   uint32_t * s_off = s_cnt + max_rings;
   __shared__ uint32_t s_work_base, s_n_present;
@@ -210,55 +265,66 @@ k_ring_plan(const ScanDesc * __restrict__ scans, uint32_t * __restrict__ tile_hi
 // ------------------------------------------------------------------ ingest: stable scatter (one CTA per tile)
 
 __global__ void __launch_bounds__(INGEST_THREADS)
-k_ring_scatter(const ScanDesc * __restrict__ scans, int n_scans, const uint16_t * __restrict__ ring16,
-               const uint32_t * __restrict__ tile_hist, const lfx_ring_info * __restrict__ rings,
-               uint32_t * __restrict__ idx, int max_rings)
+k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
+               const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ counters,
+               const uint16_t * __restrict__ ring16, const uint32_t * __restrict__ tile_hist,
+               const lfx_ring_info * __restrict__ rings, uint32_t * __restrict__ idx, int max_rings)
 {
   extern __shared__ uint32_t s_base[];  // [8 warps][max_rings]
   __shared__ int s_scan;
+  __shared__ uint32_t s_tile;
   constexpr int WARPS = INGEST_THREADS / 32;
   constexpr int PER_WARP = TILE / WARPS;   // 256 consecutive points
   constexpr int CHUNKS = PER_WARP / 32;    // 8
-  const uint32_t tile = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) { s_scan = find_scan_of_tile(scans, n_scans, tile); }
-  for (int r = threadIdx.x; r < WARPS * max_rings; r += blockDim.x) { s_base[r] = 0; }
-  __syncthreads();
-  const int scan = s_scan;
-  const ScanDesc sd = scans[scan];
-  const uint32_t first = (tile - sd.tile_base) * TILE + warp * PER_WARP;
-  uint32_t * my = s_base + warp * max_rings;
+  const uint32_t n_tiles = counters[C_GEN_TILES];
+  const int n_gen = (int)counters[C_GEN_SCANS];
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int k = find_gen_scan(gen_tile_base, n_gen, t);
+      s_scan = (int)gen_scan[k];
+      s_tile = scans[s_scan].tile_base + (t - gen_tile_base[k]);
+    }
+    for (int r = threadIdx.x; r < WARPS * max_rings; r += blockDim.x) { s_base[r] = 0; }
+    __syncthreads();
+    const int scan = s_scan;
+    const uint32_t tile = s_tile;
+    const ScanDesc sd = scans[scan];
+    const uint32_t first = (tile - sd.tile_base) * TILE + warp * PER_WARP;
+    uint32_t * my = s_base + warp * max_rings;
 
-  uint32_t ring[CHUNKS];
+    uint32_t ring[CHUNKS];
 #pragma unroll
-  for (int c = 0; c < CHUNKS; c++) {
-    const uint32_t i = first + c * 32 + lane;
-    ring[c] = i < sd.n_points ? (uint32_t)ring16[sd.point_base + i] : 0xFFFFFFFFu;
-    if (ring[c] != 0xFFFFFFFFu) { atomicAdd(&my[ring[c]], 1u); }
-  }
-  __syncthreads();
-  // per ring: running prefix over the 8 warps, seeded with the tile's stable base inside the ring bucket
-  for (int r = threadIdx.x; r < max_rings; r += blockDim.x) {
-    uint32_t run = rings[(size_t)scan * max_rings + r].offset + tile_hist[(size_t)tile * max_rings + r];
-    for (int w = 0; w < WARPS; w++) {
-      const uint32_t c = s_base[w * max_rings + r];
-      s_base[w * max_rings + r] = run;
-      run += c;
+    for (int c = 0; c < CHUNKS; c++) {
+      const uint32_t i = first + c * 32 + lane;
+      ring[c] = i < sd.n_points ? (uint32_t)ring16[sd.point_base + i] : 0xFFFFFFFFu;
+      if (ring[c] != 0xFFFFFFFFu) { atomicAdd(&my[ring[c]], 1u); }
     }
-  }
-  __syncthreads();
+    __syncthreads();
+    // per ring: running prefix over the 8 warps, seeded with the tile's stable base inside the ring bucket
+    for (int r = threadIdx.x; r < max_rings; r += blockDim.x) {
+      uint32_t run = rings[(size_t)scan * max_rings + r].offset + tile_hist[(size_t)tile * max_rings + r];
+      for (int w = 0; w < WARPS; w++) {
+        const uint32_t c = s_base[w * max_rings + r];
+        s_base[w * max_rings + r] = run;
+        run += c;
+      }
+    }
+    __syncthreads();
 #pragma unroll
-  for (int c = 0; c < CHUNKS; c++) {
-    const uint32_t i = first + c * 32 + lane;
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ring[c]);
-    if (ring[c] != 0xFFFFFFFFu) {
-      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-      const uint32_t base = my[ring[c]];
-      __syncwarp(peers);
-      if (rank == 0) { my[ring[c]] = base + __popc(peers); }
-      idx[sd.point_base + base + rank] = i;
+    for (int c = 0; c < CHUNKS; c++) {
+      const uint32_t i = first + c * 32 + lane;
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ring[c]);
+      if (ring[c] != 0xFFFFFFFFu) {
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t base = my[ring[c]];
+        __syncwarp(peers);
+        if (rank == 0) { my[ring[c]] = base + __popc(peers); }
+        idx[sd.point_base + base + rank] = i;
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 

@@ -99,7 +99,7 @@ __device__ __forceinline__ RingSmem carve_ring(unsigned char * base, int cap, in
   return s;
 }
 
-enum Misc { N_CNT_ASC = 1, N_POS_NONASC = 2, N_POS_ASC = 3, N_SKIP = 4, N_BADRING = 5 };
+enum Misc { N_CNT_ASC = 1, N_POS_NONASC = 2, N_POS_ASC = 3, N_SKIP = 4, N_BADRING = 5, N_CNT_DESC = 6, N_POS_NONDESC = 7 };
 
 __device__ __forceinline__ int pslot(int q) { return q ^ ((q >> 3) & 7); }
 __device__ __forceinline__ int dslot(int p) { return p + (p >> 4); }
@@ -315,7 +315,7 @@ k_extract_rings(const RingArgs a)
 
   for (uint32_t it = 0; w < n_work; it++, w += G) {
     // ---- top of ring `it`: its xyz (issued one ring ago) and the descriptors of ring it+1 have landed
-    if (tid < 16) { s.misc[tid] = (tid == N_POS_NONASC || tid == N_POS_ASC) ? -1 : 0; }
+    if (tid < 16) { s.misc[tid] = (tid == N_POS_NONASC || tid == N_POS_ASC || tid == N_POS_NONDESC) ? -1 : 0; }
     for (int k = tid; k < data_words; k += T) { arr(A_SB)[1 + k] = 0; }
     cp_async_wait_all();
     __syncthreads();
@@ -349,11 +349,12 @@ k_extract_rings(const RingArgs a)
     }
 
     // ---- phase 1: polar-angle order (SortByAtan2, ring.hpp:101-112). One exact comparator evaluation per
-    //      cyclic neighbour pair decides whether the ring already is a rotated ascending (n-1 ascents) or
-    //      rotated descending (<= 1 ascent) sequence. For sources addressed by (first, stride) the ring
+    //      cyclic neighbour pair and direction decides whether the ring already is a rotated strictly
+    //      ascending (n-1 ascents) or rotated strictly descending (n-1 descents) sequence; ties (equal
+    //      angles) go to the sort, which keeps source order among them like the oracle's stable sort. For sources addressed by (first, stride) the ring
     //      field of every point is checked here as well (the lines were just fetched: L2 hits).
     {
-      int cnt = 0, pos_na = -1, pos_a = -1, bad_ring = 0;
+      int cnt = 0, cntd = 0, pos_na = -1, pos_nd = -1, bad_ring = 0;
       uint32_t rid[PTS];
       if (meta.src.y) {
 #pragma unroll
@@ -372,9 +373,11 @@ k_extract_rings(const RingArgs a)
           if (q < n) {
             const int q1 = q + 1 == n ? 0 : q + 1;
             const float4 pa = pts[pslot(q)], pb = pts[pslot(q1)];
-            const bool asc = polar_less(pa.x, pa.y, pb.x, pb.y);
+            const bool asc = polar_less(pa.x, pa.y, pb.x, pb.y), desc = polar_less(pb.x, pb.y, pa.x, pa.y);
             cnt += asc ? 1 : 0;
-            if (asc) { pos_a = q; } else { pos_na = q; }   // q grows with m: keeps the largest
+            cntd += desc ? 1 : 0;
+            if (!asc) { pos_na = q; }    // q grows with m: keeps the largest
+            if (!desc) { pos_nd = q; }
           }
         }
       }
@@ -385,14 +388,16 @@ k_extract_rings(const RingArgs a)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        cntd += __shfl_xor_sync(0xFFFFFFFFu, cntd, o);
         pos_na = max(pos_na, __shfl_xor_sync(0xFFFFFFFFu, pos_na, o));
-        pos_a = max(pos_a, __shfl_xor_sync(0xFFFFFFFFu, pos_a, o));
+        pos_nd = max(pos_nd, __shfl_xor_sync(0xFFFFFFFFu, pos_nd, o));
         bad_ring |= __shfl_xor_sync(0xFFFFFFFFu, bad_ring, o);
       }
       if (lane == 0) {
         if (cnt) { atomicAdd(&s.misc[N_CNT_ASC], cnt); }
+        if (cntd) { atomicAdd(&s.misc[N_CNT_DESC], cntd); }
         if (pos_na >= 0) { atomicMax(&s.misc[N_POS_NONASC], pos_na); }
-        if (pos_a >= 0) { atomicMax(&s.misc[N_POS_ASC], pos_a); }
+        if (pos_nd >= 0) { atomicMax(&s.misc[N_POS_NONDESC], pos_nd); }
         if (bad_ring) { s.misc[N_BADRING] = 1; }
       }
       __syncthreads();
@@ -409,9 +414,10 @@ k_extract_rings(const RingArgs a)
     om.mode = 0; om.start = 0;
     int order_path = a.force_order_path;
     if (order_path == 0) {
-      const int cnt_asc = s.misc[N_CNT_ASC];
-      if (cnt_asc == n - 1) { om.mode = 0; om.start = s.misc[N_POS_NONASC] + 1; if (om.start >= n) { om.start -= n; } }
-      else if (cnt_asc <= 1) { om.mode = 1; om.start = cnt_asc == 1 ? s.misc[N_POS_ASC] : 0; }
+      const int cnt_asc = s.misc[N_CNT_ASC], cnt_desc = s.misc[N_CNT_DESC];
+      if (n == 1) { om.mode = 0; om.start = 0; }
+      else if (cnt_asc == n - 1) { om.mode = 0; om.start = s.misc[N_POS_NONASC] + 1; if (om.start >= n) { om.start -= n; } }
+      else if (cnt_desc == n - 1) { om.mode = 1; om.start = s.misc[N_POS_NONDESC]; }
       else { order_path = 1; }
     }
     if (order_path >= 1) {

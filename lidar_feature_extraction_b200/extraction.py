@@ -310,11 +310,17 @@ class FeatureExtraction:
         return {"scan_edge": xyz_msg(out.edge_xyz, out.n_edge), "scan_surface": xyz_msg(out.surface_xyz, out.n_surface),
                 "labels": labels, "stamp": msg.stamp, "frame_id": FRAME_ID}
 
+    def batch_stats(self) -> dict:
+        """Which path the last batch took: rings on the sector kernel per lane class, scans/rings on the general path."""
+        st = N.BatchStats()
+        self._check(self._lib.lfx_last_batch_stats(self._h, C.byref(st)))
+        return {"fast_rings": list(st.fast_rings), "general_scans": int(st.general_scans), "general_rings": int(st.general_rings)}
+
     # -- stage timing
     def set_stage_timing(self, enabled: bool):
         self._check(self._lib.lfx_set_stage_timing(self._h, int(enabled)))
 
     def last_stage_ms(self):
-        ms = (C.c_float * 3)()
+        ms = (C.c_float * 4)()
         self._check(self._lib.lfx_last_stage_ms(self._h, ms))
         return tuple(ms)
