@@ -59,7 +59,7 @@ struct lfx_handle
   int ring_threads = 0;
   void (*ring_kernel)(const RingArgs) = nullptr;
   void (*sector_kernel[N_FAST_K])(const SectorArgs) = {nullptr, nullptr, nullptr};  // null: no fast path for these parameters
-  int sector_grid = 0, ingest_grid = 0;
+  int sector_grid[N_FAST_K] = {0, 0, 0}, ingest_grid = 0;
   size_t sector_smem[N_FAST_K] = {0, 0, 0};
   bool fast_enabled = false;
   cudaStream_t stream = nullptr;
@@ -202,9 +202,9 @@ void (*pick_ring_kernel(int padding, int threads, int * tmax))(const RingArgs)
 template<int P, bool DIAG>
 void pick_sector_kernels_t(void (**out)(const SectorArgs))
 {
-  out[0] = k_extract_sectors<P, fast_k(0), DIAG, SEC_WARPS>;
-  out[1] = k_extract_sectors<P, fast_k(1), DIAG, SEC_WARPS>;
-  out[2] = k_extract_sectors<P, fast_k(2), DIAG, SEC_WARPS>;
+  out[0] = k_extract_sectors<P, fast_k(0), DIAG>;
+  out[1] = k_extract_sectors<P, fast_k(1), DIAG>;
+  out[2] = k_extract_sectors<P, fast_k(2), DIAG>;
 }
 
 // The sector kernel is compiled for the two deployed paddings (compiled default 5, launch YAML 2);
@@ -262,8 +262,9 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       sa.curvature = h->opt.want_curvature ? h->d_curv.p : nullptr;
       sa.stage = h->d_stage.p;
       sa.max_rings = max_rings;
+      sa.inv_blocks = (uint32_t)(0x100000000ull / (uint64_t)h->params.n_blocks);
       sa.prm = h->dev;
-      h->sector_kernel[c]<<<h->sector_grid, SEC_WARPS * 32, h->sector_smem[c], h->stream>>>(sa);
+      h->sector_kernel[c]<<<h->sector_grid[c], sector_warps(fast_k(c)) * 32, h->sector_smem[c], h->stream>>>(sa);
     }
   }
   if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
@@ -442,16 +443,15 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->fast_enabled = h->opt.force_order_path == 0 && params->n_blocks <= FAST_MAX_BLOCKS &&
                     pick_sector_kernels(params->padding, h->opt.want_sorted_src || h->opt.want_curvature, h->sector_kernel);
   if (h->fast_enabled) {
-    h->sector_smem[0] = sector_smem_bytes<fast_k(0)>(SEC_WARPS);
-    h->sector_smem[1] = sector_smem_bytes<fast_k(1)>(SEC_WARPS);
-    h->sector_smem[2] = sector_smem_bytes<fast_k(2)>(SEC_WARPS);
-    int socc = 0;
+    h->sector_smem[0] = sector_smem_bytes<fast_k(0)>(sector_warps(fast_k(0)));
+    h->sector_smem[1] = sector_smem_bytes<fast_k(1)>(sector_warps(fast_k(1)));
+    h->sector_smem[2] = sector_smem_bytes<fast_k(2)>(sector_warps(fast_k(2)));
     for (int c = 0; c < N_FAST_K; c++) {
       if ((e = cudaFuncSetAttribute(h->sector_kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sector_smem[c])) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(sectors)"); }
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], SEC_WARPS * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
-      socc = std::max(socc, occ);
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c)) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
+      if (occ < 1) { g_create_error = "sector kernel does not fit on this device"; lfx_destroy(h); return LFX_E_CUDA; }
+      h->sector_grid[c] = h->num_sms * occ;
     }
-    h->sector_grid = h->num_sms * std::max(socc, 1);
   }
   const size_t probe_smem = sizeof(uint32_t) * (3 * (size_t)h->opt.max_rings + 1);
   if (probe_smem > 48 * 1024) {

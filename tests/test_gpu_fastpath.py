@@ -109,7 +109,10 @@ def test_sparse_ring_ids_and_ring_datatypes(oracle):
     assert stats["general_scans"] == 0 and sum(stats["fast_rings"]) == 5
     x, y, z, _, ring = (np.ascontiguousarray(a) for a in synth.fields(base))
     want = oracle.extract_scan(base, oracle_params(ob, hp))
-    for step, ox, oring, rdt, npdt in ((48, 16, 44, 6, np.uint32), (32, 0, 13, 2, np.uint8), (64, 32, 2, 4, np.uint16)):
+    # (point_step, x offset, ring offset, ring datatype): ring in the chunk after x,y,z,w / inside it / before it /
+    # too far away from it for the sector kernel's staging (that layout takes the general path)
+    for step, ox, oring, rdt, npdt, fast in ((48, 16, 44, 6, np.uint32, True), (32, 0, 13, 2, np.uint8, True),
+                                             (64, 32, 18, 4, np.uint16, True), (64, 32, 2, 4, np.uint16, False)):
         buf = np.zeros((len(x), step), np.uint8)
         for k, a in enumerate((x, y, z)):
             buf[:, ox + 4 * k: ox + 4 * k + 4] = a.view(np.uint8).reshape(-1, 4)
@@ -121,7 +124,7 @@ def test_sparse_ring_ids_and_ring_datatypes(oracle):
             out = fe.extract_batch([msg])
             st = fe.batch_stats()
         compare_scan(out, 0, base, want)
-        assert st["general_scans"] == 0, (step, st)
+        assert st["general_scans"] == (0 if fast else 1), (step, oring, st)
 
 
 def _points(cloud):
