@@ -12,7 +12,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-LIB_PATH = os.path.join(PKG_DIR, "liblfx.so")
+LIB_PATH = os.environ.get("LFX_LIB") or os.path.join(PKG_DIR, "liblfx.so")  # LFX_LIB: A/B builds of the same ABI
 HEADER = os.path.join(ROOT, "include", "lfx.h")
 
 LFX_OK, LFX_E_BAD_PARAM, LFX_E_NOT_DENSE, LFX_E_NO_RING, LFX_E_BAD_LAYOUT, LFX_E_CAPACITY, LFX_E_CUDA, LFX_E_STATE = range(8)
