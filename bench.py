@@ -190,7 +190,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, synth
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, sharding, synth
     from lidar_feature_extraction_b200 import _native as N
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,7 +211,9 @@ def main():
         scans_per_gpu = args.scans
     sp = synth.spec(sensor)
     per_scan = sp.n_rings * sp.n_cols
-    first_frame = rank * scans_per_gpu  # shard frames by index: rank g owns [g*F/G, (g+1)*F/G)
+    n_frames = world * scans_per_gpu    # weak scaling: the per-GPU shard is fixed
+    first_frame, last_frame = sharding.shard_range(n_frames, rank, world)  # rank g owns [g*F/G, (g+1)*F/G)
+    assert last_frame - first_frame == scans_per_gpu
 
     stream = torch.cuda.current_stream(dev)
     fe = FeatureExtraction(HyperParameters(), device=local_rank, stream=stream.cuda_stream,
@@ -232,15 +234,12 @@ def main():
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n_points = int(offs[-1])
     dev_views = [FeatureExtraction.wire_view((d_in.data_ptr() + int(offs[s]) * 32, sizes[s])) for s in range(scans_per_gpu)]
-    counts_all = torch.empty((world, scans_per_gpu, 2), dtype=torch.int32, device=dev) if world > 1 else None
-
     def step_device():
         res = fe.extract_views(dev_views, keep=d_in)
         if world > 1:
-            # the path's only exchange: all-gather of per-scan (n_edge, n_surface) over NVLink; global
-            # offsets follow from a local exclusive scan
-            cnt = _as_tensor(torch, res.d_counts, (scans_per_gpu, 2), dev)
-            dist.all_gather_into_tensor(counts_all.view(world * scans_per_gpu, 2), cnt)
+            # the path's only exchange: all-gather of per-scan (n_edge, n_surface) over NVLink, enqueued on
+            # the extraction stream; global offsets follow from a local exclusive scan
+            sharding.gather_counts(sharding.device_counts_tensor(res, dev), n_frames)
         return res
 
     for _ in range(max(args.warmup, 3)):
@@ -320,8 +319,7 @@ def main():
         def step_e2e():
             res = fe.extract_views(host_views)
             if world > 1:
-                cnt = _as_tensor(torch, res.d_counts, (scans_per_gpu, 2), dev)
-                dist.all_gather_into_tensor(counts_all.view(world * scans_per_gpu, 2), cnt)
+                sharding.gather_counts(sharding.device_counts_tensor(res, dev), n_frames)
             rc = lib.lfx_fetch_counts(fe.handle, h_counts.ctypes.data, h_offsets.ctypes.data)
             rc |= lib.lfx_fetch_features(fe.handle, h_edge, 2 * max(n_feat, 1), h_surf, 2 * max(n_feat, 1))
             assert rc == 0, rc
@@ -377,17 +375,6 @@ def main():
     fe.close()
     if world > 1:
         dist.destroy_process_group()
-
-
-def _as_tensor(torch, ptr: int, shape, dev):
-    """Wrap a device pointer owned by the library as an int32 tensor (no copy) via __cuda_array_interface__."""
-
-    class _W:
-        pass
-
-    w = _W()
-    w.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 3, "strides": None}
-    return torch.as_tensor(w, device=dev)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,101 @@
+// lfx.hpp — header-only C++17 host mirror of the reference extraction node's state over the C ABI (lfx.h).
+//
+// Mirrors, for the one path this library replaces:
+//   lfx::HyperParameters   extraction/include/lidar_feature_extraction/hyper_parameter.hpp:32-65
+//   lfx::FeatureExtraction the per-scan work of FeatureExtraction::Callback, extraction/app/feature_extraction.cpp:92-171
+// No CUDA or ROS headers are needed to include this file; link with -llfx.
+#ifndef LFX_HPP_
+#define LFX_HPP_
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "lfx.h"
+
+namespace lfx
+{
+
+struct Error : std::runtime_error
+{
+  int code;
+  Error(int c, const std::string & what) : std::runtime_error(what), code(c) {}
+};
+
+// hyper_parameter.hpp:35-43: same nine names, same defaults
+struct HyperParameters : lfx_params
+{
+  HyperParameters() { lfx_default_params(this); }
+  static HyperParameters LaunchYaml() { HyperParameters p; lfx_launch_yaml_params(&p); return p; }
+};
+
+// One field of sensor_msgs/PointCloud2::fields, as much as the callback reads of it
+struct PointField { std::string name; uint32_t offset; uint8_t datatype; };
+
+// Field lookup by name, as pcl::fromROSMsg does for PointXYZIR (lib/include/lidar_feature_library/point_type.hpp:83-86).
+// RingIsAvailable (ring.cpp:36-44) becomes view.has_ring; is_dense is taken from the message.
+inline lfx_cloud_view MakeView(const void * data, uint32_t n_points, uint32_t point_step, const std::vector<PointField> & fields,
+                               bool is_dense, bool device_memory = false)
+{
+  lfx_cloud_view v;
+  std::memset(&v, 0, sizeof(v));
+  v.data = data;
+  v.n_points = n_points;
+  v.point_step = point_step;
+  v.is_dense = is_dense ? 1 : 0;
+  v.memory = device_memory ? LFX_MEM_DEVICE : LFX_MEM_HOST;
+  v.ring_datatype = LFX_RING_U16;
+  int have = 0;
+  for (const auto & f : fields) {
+    if (f.name == "x") { v.off_x = f.offset; have |= 1; }
+    else if (f.name == "y") { v.off_y = f.offset; have |= 2; }
+    else if (f.name == "z") { v.off_z = f.offset; have |= 4; }
+    else if (f.name == "ring") { v.off_ring = f.offset; v.ring_datatype = f.datatype; v.has_ring = 1; }
+  }
+  if (have != 7) { throw Error(LFX_E_BAD_LAYOUT, "PointCloud2 lacks x, y or z"); }
+  return v;
+}
+
+class FeatureExtraction
+{
+public:
+  explicit FeatureExtraction(const HyperParameters & params = HyperParameters(), int device = 0)
+  {
+    lfx_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    opt.device = device;
+    const int rc = lfx_create(&params, &opt, &h_);
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(nullptr)); }
+  }
+  ~FeatureExtraction() { lfx_destroy(h_); }
+  FeatureExtraction(const FeatureExtraction &) = delete;
+  FeatureExtraction & operator=(const FeatureExtraction &) = delete;
+
+  // One scan, synchronous: what the callback needs to fill scan_edge / scan_surface (16-byte x,y,z,1 points,
+  // pinned host memory owned by the handle, valid until the next call) and colored_scan (labels).
+  lfx_scan_output Extract(const lfx_cloud_view & scan)
+  {
+    lfx_scan_output out;
+    Check(lfx_extract_scan(h_, &scan, &out));
+    return out;
+  }
+
+  // Many independent scans, asynchronous (offline map building): results stay on the device.
+  lfx_batch_result ExtractBatch(const std::vector<lfx_cloud_view> & scans)
+  {
+    lfx_batch_result res;
+    Check(lfx_extract_batch(h_, scans.data(), static_cast<int>(scans.size()), &res));
+    return res;
+  }
+  void Synchronize() { Check(lfx_synchronize(h_)); }
+  lfx_handle * handle() { return h_; }
+
+private:
+  void Check(int rc) { if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); } }
+  lfx_handle * h_ = nullptr;
+};
+
+}  // namespace lfx
+#endif  // LFX_HPP_

@@ -94,3 +94,48 @@ def test_synthetic_generator_shapes_and_determinism():
             assert len(np.unique(az[:, k])) == w
     hd = synth.scan_host(synth.spec("hdl64"), 0)
     assert 0 < len(hd) < 64 * 2048                                   # drop-outs make it ragged
+
+
+def test_cpp_host_mirror_compiles_links_and_fails_loudly(tmp_path):
+    """include/lfx.hpp (the C++ side of the boundary) against the built library: parameter mirror, field
+    lookup by name, and - on a box without a GPU - LFX_E_CUDA from the constructor instead of any fallback."""
+    import shutil
+    import subprocess
+
+    import torch
+
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "lfx.hpp"
+int main() {
+  lfx::HyperParameters d;
+  lfx::HyperParameters y = lfx::HyperParameters::LaunchYaml();
+  if (d.padding != 5 || d.n_blocks != 6 || y.padding != 2 || y.edge_threshold != 50.0) { return 10; }
+  std::vector<lfx::PointField> f = {{"x", 0, 7}, {"y", 4, 7}, {"z", 8, 7}, {"intensity", 16, 7}, {"ring", 20, LFX_RING_U16}};
+  float buf[8] = {1, 2, 3, 1, 0, 0, 0, 0};
+  lfx_cloud_view v = lfx::MakeView(buf, 1, 32, f, true);
+  if (!v.has_ring || v.off_ring != 20 || v.off_y != 4 || v.ring_datatype != LFX_RING_U16) { return 11; }
+  f.pop_back();
+  if (lfx::MakeView(buf, 1, 32, f, true).has_ring) { return 12; }   // RingIsAvailable, ring.cpp:36-44
+  try {
+    lfx::FeatureExtraction fe(d, 0);
+    lfx_scan_output out = fe.Extract(v);                                // a GPU is present: one sparse ring, no features
+    std::printf("gpu n_edge=%u n_surface=%u\n", out.n_edge, out.n_surface);
+    return (out.n_edge == 0 && out.n_surface == 0) ? 0 : 13;
+  } catch (const lfx::Error & e) {
+    std::printf("error %d: %s\n", e.code, e.what());
+    return e.code == LFX_E_CUDA ? 42 : 14;
+  }
+}
+''')
+    exe = tmp_path / "host"
+    pkg = os.path.join(root, "lidar_feature_extraction_b200")
+    subprocess.run([cxx, "-std=c++17", "-Wall", "-Werror", f"-I{root}/include", str(src), "-o", str(exe),
+                    f"-L{pkg}", "-llfx", f"-Wl,-rpath,{pkg}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == (0 if torch.cuda.is_available() else 42), (r.returncode, r.stdout, r.stderr)
