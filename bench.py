@@ -288,7 +288,8 @@ def main():
     achieved = alg_bytes / (ring_ms * 1e-3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "ring_kernel_traffic.json")) as f:
+        # dram__bytes_read + dram__bytes_write of one launch of the sector kernel (ncu --set full), per point
+        with open(os.path.join(ROOT, "profiles", "sector_kernel_traffic.json")) as f:
             tj = json.load(f)
         traffic = float(tj["dram_bytes_per_point"][sensor]) * n_points
     except Exception:
