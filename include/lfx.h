@@ -213,20 +213,24 @@ int lfx_memcpy_d2h(lfx_handle *h, void *dst_host, const void *src_device, size_t
 /* Kernels launched / graph launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t lfx_kernel_launch_count(const lfx_handle *h);
 /* Device time of the last batch's stages, measured with CUDA events on the handle's stream:
- * ms[0]=layout probe, ms[1]=sector kernel (fast path), ms[2]=general path (list + hist + plan +
- * scatter + ring kernel), ms[3]=pack. Only when timing was enabled. */
+ * ms[0]=layout probe, ms[1]=sector kernel on regular scans, ms[2]=ring bucketing of the other scans (list +
+ * hist + plan + scatter + ring probe), ms[3]=sector kernel on bucketed rings, ms[4]=per-ring (sort) kernel,
+ * ms[5]=pack. Only when timing was enabled. */
+#define LFX_N_STAGES 6
 int lfx_set_stage_timing(lfx_handle *h, int enabled);
-int lfx_last_stage_ms(lfx_handle *h, float *ms4);
+int lfx_last_stage_ms(lfx_handle *h, float *ms /* [LFX_N_STAGES] */);
 
 /* Which path the scans of the last batch took (synchronises). A scan is "regular" when its points are
  * in sensor firing order with a fixed ring period and every ring is a rotated monotone sequence of polar
- * angles; regular scans run on the sector kernel, everything else (and every scan that fails one of the
- * sector kernel's checks) on the general bucket + sort + ring kernel. Results are identical. */
+ * angles; regular scans run on the sector kernel straight from the PointCloud2 payload. Every other scan
+ * (returns dropped by the converter, arbitrary point order, or a failed check) is bucketed by ring id first;
+ * its rings that are rotated monotone sequences run on the same sector kernel through the bucket's index
+ * list, the remaining rings are sorted and processed by the per-ring kernel. Results are identical. */
 typedef struct lfx_batch_stats {
-  uint32_t fast_rings[3];   /* rings handed to the sector kernel, per positions-per-lane class (10, 11, 12) */
-  uint32_t general_scans;   /* scans that took the general path */
-  uint32_t general_rings;   /* rings processed by the general ring kernel */
-  uint32_t reserved[3];
+  uint32_t fast_rings[3];   /* rings of regular scans handed to the sector kernel, per positions-per-lane class (10, 11, 12) */
+  uint32_t general_scans;   /* scans that were bucketed by ring id */
+  uint32_t general_rings;   /* rings processed by the per-ring (sort) kernel */
+  uint32_t indexed_rings[3];/* bucketed rings handed to the sector kernel, per class */
 } lfx_batch_stats;
 int lfx_last_batch_stats(lfx_handle *h, lfx_batch_stats *out);
 

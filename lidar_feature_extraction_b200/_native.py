@@ -111,7 +111,7 @@ class ScanOutput(C.Structure):
 
 class BatchStats(C.Structure):
     _fields_ = [("fast_rings", C.c_uint32 * 3), ("general_scans", C.c_uint32), ("general_rings", C.c_uint32),
-                ("reserved", C.c_uint32 * 3)]
+                ("indexed_rings", C.c_uint32 * 3)]
 
 
 class SynthSpec(C.Structure):

@@ -58,9 +58,10 @@ struct lfx_handle
   int cap = 0;
   int ring_threads = 0;
   void (*ring_kernel)(const RingArgs) = nullptr;
-  void (*sector_kernel[N_FAST_K])(const SectorArgs) = {nullptr, nullptr, nullptr};  // null: no fast path for these parameters
-  int sector_grid[N_FAST_K] = {0, 0, 0}, ingest_grid = 0;
-  size_t sector_smem[N_FAST_K] = {0, 0, 0};
+  // [0..2]: regular scans (strided rings), [3..5]: indexed rings of bucketed scans; null: no fast path for these parameters
+  void (*sector_kernel[2 * N_FAST_K])(const SectorArgs) = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int sector_grid[2 * N_FAST_K] = {0, 0, 0, 0, 0, 0}, ingest_grid = 0;
+  size_t sector_smem[2 * N_FAST_K] = {0, 0, 0, 0, 0, 0};
   bool fast_enabled = false;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -78,8 +79,10 @@ struct lfx_handle
   DevBuf<uint2> d_ring_src;
   DevBuf<uint32_t> d_scan_flags;
   DevBuf<uint32_t> d_gen_scan, d_gen_tile_base;
-  DevBuf<FastRing> d_fast[N_FAST_K];
-  DevBuf<SectorRec> d_rec[N_FAST_K];
+  DevBuf<FastRing> d_fast[2 * N_FAST_K];
+  DevBuf<SectorRec> d_rec[2 * N_FAST_K];
+  DevBuf<int> d_bndx[N_FAST_K];
+  DevBuf<uint32_t> d_ring_path;
   DevBuf<uint32_t> d_idx;
   DevBuf<uint8_t> d_labels;
   DevBuf<uint32_t> d_sorted_src;
@@ -109,7 +112,7 @@ struct lfx_handle
   bool have_batch = false;
 
   bool timing = false;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[LFX_N_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have_timing = false;
 };
 
@@ -202,9 +205,12 @@ void (*pick_ring_kernel(int padding, int threads, int * tmax))(const RingArgs)
 template<int P, bool DIAG>
 void pick_sector_kernels_t(void (**out)(const SectorArgs))
 {
-  out[0] = k_extract_sectors<P, fast_k(0), DIAG>;
-  out[1] = k_extract_sectors<P, fast_k(1), DIAG>;
-  out[2] = k_extract_sectors<P, fast_k(2), DIAG>;
+  out[0] = k_extract_sectors<P, fast_k(0), DIAG, false>;
+  out[1] = k_extract_sectors<P, fast_k(1), DIAG, false>;
+  out[2] = k_extract_sectors<P, fast_k(2), DIAG, false>;
+  out[3] = k_extract_sectors<P, fast_k(0), DIAG, true>;
+  out[4] = k_extract_sectors<P, fast_k(1), DIAG, true>;
+  out[5] = k_extract_sectors<P, fast_k(2), DIAG, true>;
 }
 
 // The sector kernel is compiled for the two deployed paddings (compiled default 5, launch YAML 2);
@@ -253,7 +259,11 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
     for (int c = 0; c < N_FAST_K; c++) {
       SectorArgs sa;
       sa.fast = h->d_fast[c].p;
+      sa.bnd = nullptr;
       sa.n_entries = h->d_counters + C_N_FAST0 + c;
+      sa.ring_path = nullptr;
+      sa.work = nullptr;
+      sa.counters = h->d_counters;
       sa.rec = h->d_rec[c].p;
       sa.rings = h->d_rings.p;
       sa.scan_flags = h->d_scan_flags.p;
@@ -274,10 +284,49 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   k_ring_hist<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
     h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
   k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
-    h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, h->d_work.p, h->d_counters, max_rings,
-    h->params.padding, h->cap);
+    h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, max_rings, h->params.padding, h->cap);
   k_ring_scatter<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
     h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
+  // ---- bucketed rings that are rotated monotone sequences: sector kernel through the index list; the rest
+  //      (and every ring whose hypothesis fails there) form the work list of the per-ring kernel
+  RingProbeArgs rp;
+  rp.scans = h->d_scans.p;
+  rp.gen_scan = h->d_gen_scan.p;
+  rp.idx = h->d_idx.p;
+  rp.rings = h->d_rings.p;
+  for (int c = 0; c < N_FAST_K; c++) { rp.fastx[c] = h->d_fast[N_FAST_K + c].p; rp.bndx[c] = h->d_bndx[c].p; }
+  rp.ring_path = h->d_ring_path.p;
+  rp.work = h->d_work.p;
+  rp.counters = h->d_counters;
+  rp.max_rings = max_rings;
+  rp.P = h->params.padding;
+  rp.B = h->params.n_blocks;
+  rp.enabled = h->fast_enabled ? 1 : 0;
+  k_probe_rings<<<n_scans, PROBE_THREADS, sizeof(uint32_t) * 3 * max_rings, h->stream>>>(rp);
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[3], h->stream)); }
+  if (h->fast_enabled) {
+    for (int c = 0; c < N_FAST_K; c++) {
+      SectorArgs sa;
+      sa.fast = h->d_fast[N_FAST_K + c].p;
+      sa.bnd = h->d_bndx[c].p;
+      sa.n_entries = h->d_counters + C_N_FASTX0 + c;
+      sa.ring_path = h->d_ring_path.p;
+      sa.work = h->d_work.p;
+      sa.counters = h->d_counters;
+      sa.rec = h->d_rec[N_FAST_K + c].p;
+      sa.rings = h->d_rings.p;
+      sa.scan_flags = h->d_scan_flags.p;
+      sa.labels = h->d_labels.p;
+      sa.sorted_src = h->opt.want_sorted_src ? h->d_sorted_src.p : nullptr;
+      sa.curvature = h->opt.want_curvature ? h->d_curv.p : nullptr;
+      sa.stage = h->d_stage.p;
+      sa.max_rings = max_rings;
+      sa.inv_blocks = (uint32_t)(0x100000000ull / (uint64_t)h->params.n_blocks);
+      sa.prm = h->dev;
+      h->sector_kernel[N_FAST_K + c]<<<h->sector_grid[N_FAST_K + c], sector_warps(fast_k(c)) * 32, h->sector_smem[N_FAST_K + c], h->stream>>>(sa);
+    }
+  }
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[4], h->stream)); }
   RingArgs ra;
   ra.scans = h->d_scans.p;
   ra.idx = h->d_idx.p;
@@ -295,15 +344,16 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   ra.force_order_path = h->opt.force_order_path;
   ra.prm = h->dev;
   h->ring_kernel<<<h->ring_grid, h->ring_threads, h->ring_smem, h->stream>>>(ra);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[3], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[5], h->stream)); }
   // ---- packing
   k_feat_offsets_a<<<n_scans, 128, 0, h->stream>>>(h->d_rings.p, h->d_ring_featoff.p, h->d_counts.p, max_rings);
   k_feat_offsets_b<<<1, 1024, 0, h->stream>>>(h->d_counts.p, h->d_offsets.p, n_scans);
   if (h->fast_enabled) {
     PackFastArgs pf;
-    for (int c = 0; c < N_FAST_K; c++) { pf.fast[c] = h->d_fast[c].p; pf.rec[c] = h->d_rec[c].p; }
+    for (int c = 0; c < 2 * N_FAST_K; c++) { pf.fast[c] = h->d_fast[c].p; pf.rec[c] = h->d_rec[c].p; }
     pf.counters = h->d_counters;
     pf.scan_flags = h->d_scan_flags.p;
+    pf.ring_path = h->d_ring_path.p;
     pf.ring_featoff = h->d_ring_featoff.p;
     pf.offsets = h->d_offsets.p;
     pf.stage = h->d_stage.p;
@@ -316,12 +366,12 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   k_pack_copy<<<h->pack_grid, 256, 0, h->stream>>>(
     h->d_work.p, h->d_counters, h->d_scans.p, h->d_rings.p, h->d_ring_featoff.p, h->d_offsets.p, h->d_stage.p,
     h->d_edge.p, h->d_surface.p, max_rings);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[4], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[6], h->stream)); }
   LFX_CUDA(h, cudaGetLastError());
   return LFX_OK;
 }
 
-int kernels_per_batch(const lfx_handle * h) { return h->fast_enabled ? 10 + N_FAST_K + 1 : 10; }
+int kernels_per_batch(const lfx_handle * h) { return h->fast_enabled ? 11 + 2 * N_FAST_K + 1 : 11; }
 
 }  // namespace
 
@@ -443,12 +493,15 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->fast_enabled = h->opt.force_order_path == 0 && params->n_blocks <= FAST_MAX_BLOCKS &&
                     pick_sector_kernels(params->padding, h->opt.want_sorted_src || h->opt.want_curvature, h->sector_kernel);
   if (h->fast_enabled) {
-    h->sector_smem[0] = sector_smem_bytes<fast_k(0)>(sector_warps(fast_k(0)));
-    h->sector_smem[1] = sector_smem_bytes<fast_k(1)>(sector_warps(fast_k(1)));
-    h->sector_smem[2] = sector_smem_bytes<fast_k(2)>(sector_warps(fast_k(2)));
-    for (int c = 0; c < N_FAST_K; c++) {
+    h->sector_smem[0] = sector_smem_bytes<fast_k(0), false>(sector_warps(fast_k(0)));
+    h->sector_smem[1] = sector_smem_bytes<fast_k(1), false>(sector_warps(fast_k(1)));
+    h->sector_smem[2] = sector_smem_bytes<fast_k(2), false>(sector_warps(fast_k(2)));
+    h->sector_smem[3] = sector_smem_bytes<fast_k(0), true>(sector_warps(fast_k(0)));
+    h->sector_smem[4] = sector_smem_bytes<fast_k(1), true>(sector_warps(fast_k(1)));
+    h->sector_smem[5] = sector_smem_bytes<fast_k(2), true>(sector_warps(fast_k(2)));
+    for (int c = 0; c < 2 * N_FAST_K; c++) {
       if ((e = cudaFuncSetAttribute(h->sector_kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sector_smem[c])) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(sectors)"); }
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c)) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c % N_FAST_K)) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
       if (occ < 1) { g_create_error = "sector kernel does not fit on this device"; lfx_destroy(h); return LFX_E_CUDA; }
       h->sector_grid[c] = h->num_sms * occ;
     }
@@ -456,6 +509,7 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   const size_t probe_smem = sizeof(uint32_t) * (3 * (size_t)h->opt.max_rings + 1);
   if (probe_smem > 48 * 1024) {
     if ((e = cudaFuncSetAttribute(k_probe_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(probe)"); }
+    if ((e = cudaFuncSetAttribute(k_probe_rings, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)probe_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(ring probe)"); }
   }
 
   if ((e = cudaMalloc(reinterpret_cast<void **>(&h->d_counters), sizeof(uint32_t) * C_COUNT)) != cudaSuccess) { return bail(e, "cudaMalloc(counters)"); }
@@ -478,7 +532,9 @@ void lfx_destroy(lfx_handle * h)
   cudaFree(h->d_labels.p); cudaFree(h->d_sorted_src.p); cudaFree(h->d_curv.p); cudaFree(h->d_stage.p);
   cudaFree(h->d_edge.p); cudaFree(h->d_surface.p); cudaFree(h->d_counts.p); cudaFree(h->d_offsets.p);
   cudaFree(h->d_input.p); cudaFree(h->d_counters); cudaFree(h->d_gen_scan.p); cudaFree(h->d_gen_tile_base.p);
-  for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
+  for (int c = 0; c < 2 * N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
+  for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_bndx[c].p); }
+  cudaFree(h->d_ring_path.p);
   cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
   for (auto & ev : h->ev) { if (ev) { cudaEventDestroy(ev); } }
@@ -550,11 +606,15 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
     size_t fast_cap = 0;
     for (int s = 0; s < n_scans; s++) { fast_cap += std::min<size_t>(scans[s].n_points / FAST_MIN_RING, mr); }
     fast_cap = std::max<size_t>(fast_cap, 1);
-    for (int c = 0; c < N_FAST_K; c++) {
+    for (int c = 0; c < 2 * N_FAST_K; c++) {
       if ((rc = ensure(h, h->d_fast[c], fast_cap, &regrown))) { return rc; }
       if ((rc = ensure(h, h->d_rec[c], fast_cap * h->params.n_blocks, &regrown))) { return rc; }
     }
+    for (int c = 0; c < N_FAST_K; c++) {
+      if ((rc = ensure(h, h->d_bndx[c], fast_cap * FAST_BND, &regrown))) { return rc; }
+    }
   }
+  if ((rc = ensure(h, h->d_ring_path, ns * mr, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_idx, np, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_labels, np, &regrown))) { return rc; }
   if (h->opt.want_sorted_src && (rc = ensure(h, h->d_sorted_src, np, &regrown))) { return rc; }
@@ -860,13 +920,13 @@ int lfx_set_stage_timing(lfx_handle * h, int enabled)
   return LFX_OK;
 }
 
-int lfx_last_stage_ms(lfx_handle * h, float * ms4)
+int lfx_last_stage_ms(lfx_handle * h, float * ms)
 {
-  if (!h || !ms4) { return LFX_E_BAD_PARAM; }
+  if (!h || !ms) { return LFX_E_BAD_PARAM; }
   if (!h->have_timing) { return fail(h, LFX_E_STATE, "stage timing was not enabled for the last batch"); }
   LFX_CUDA(h, cudaSetDevice(h->device));
-  LFX_CUDA(h, cudaEventSynchronize(h->ev[4]));
-  for (int k = 0; k < 4; k++) { LFX_CUDA(h, cudaEventElapsedTime(&ms4[k], h->ev[k], h->ev[k + 1])); }
+  LFX_CUDA(h, cudaEventSynchronize(h->ev[LFX_N_STAGES]));
+  for (int k = 0; k < LFX_N_STAGES; k++) { LFX_CUDA(h, cudaEventElapsedTime(&ms[k], h->ev[k], h->ev[k + 1])); }
   return LFX_OK;
 }
 
@@ -879,6 +939,7 @@ int lfx_last_batch_stats(lfx_handle * h, lfx_batch_stats * out)
   LFX_CUDA(h, cudaStreamSynchronize(h->stream));
   memset(out, 0, sizeof(*out));
   for (int c = 0; c < N_FAST_K; c++) { out->fast_rings[c] = h->h_counters[C_N_FAST0 + c]; }
+  for (int c = 0; c < N_FAST_K; c++) { out->indexed_rings[c] = h->h_counters[C_N_FASTX0 + c]; }
   out->general_scans = h->h_counters[C_GEN_SCANS];
   out->general_rings = h->h_counters[C_N_WORK];
   return LFX_OK;

@@ -5,8 +5,10 @@
 //                   not regular, or fail its checks, are flagged and take the general path below
 //   k_general_list  compact list of the flagged scans and their ingest tiles
 //   k_ring_hist     per 2048-point tile: ring-id histogram           (MakePointIndices, ring.hpp:114-125)
-//   k_ring_plan     per scan: stable bucket offsets, ring table, work list (+ RemoveSparseRings, ring.cpp:46-59)
+//   k_ring_plan     per scan: stable bucket offsets, ring table (+ RemoveSparseRings, ring.cpp:46-59)
 //   k_ring_scatter  per tile: stable scatter of point indices into ring buckets
+//   k_probe_rings + k_extract_sectors<indexed> (lfx_sector.cuh): bucketed rings that are rotated monotone
+//                   sequences run on the sector kernel through their index list; the rest form the work list of
 //   k_extract_rings persistent, one CTA per ring at a time: everything in feature_extraction.cpp:121-151
 //                   held in shared memory (angle order, range, curvature, link/mask bitfields,
 //                   sector-clipped greedy selection, final labels, feature staging)
@@ -35,7 +37,8 @@ enum Counter {
   C_N_WORK = 0, C_WORK_NEXT = 1, C_PACK_NEXT = 2, C_ERR_FLAG = 3, C_ERR_SCAN = 4, C_ERR_RING = 5,
   C_GEN_SCANS = 6,   // scans taking the general path (flagged by k_probe_layout or k_extract_sectors)
   C_GEN_TILES = 7,   // ingest tiles of those scans
-  C_N_FAST0 = 8,     // + kidx: entries of the fast-path ring lists
+  C_N_FAST0 = 8,     // + kidx: entries of the fast-path ring lists (regular scans)
+  C_N_FASTX0 = 11,   // + kidx: entries of the indexed ring lists (bucketed rings of flagged scans)
   C_COUNT = 16
 };
 
@@ -216,13 +219,11 @@ k_ring_hist(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ g
 
 __global__ void __launch_bounds__(256)
 k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ scan_flags, uint32_t * __restrict__ tile_hist,
-            lfx_ring_info * __restrict__ rings, uint2 * __restrict__ ring_src, uint2 * __restrict__ work, uint32_t * counters,
-            int max_rings, int padding, int cap)
+            lfx_ring_info * __restrict__ rings, uint2 * __restrict__ ring_src, int max_rings, int padding, int cap)
 {
   if (!scan_flags[blockIdx.x]) { return; }  // handled by the fast path
   extern __shared__ uint32_t s_cnt[];  // [max_rings] counts, then [max_rings] offsets
   uint32_t * s_off = s_cnt + max_rings;
-  __shared__ uint32_t s_work_base, s_n_present;
   const int scan = blockIdx.x;
   const ScanDesc sd = scans[scan];
   for (int r = threadIdx.x; r < max_rings; r += blockDim.x) {
@@ -237,10 +238,8 @@ k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ s
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t run = 0, present = 0;
-    for (int r = 0; r < max_rings; r++) { s_off[r] = run; run += s_cnt[r]; present += s_cnt[r] ? 1u : 0u; }
-    s_n_present = present;
-    s_work_base = present ? atomicAdd(&counters[C_N_WORK], present) : 0u;
+    uint32_t run = 0;
+    for (int r = 0; r < max_rings; r++) { s_off[r] = run; run += s_cnt[r]; }
   }
   __syncthreads();
   for (int r = threadIdx.x; r < max_rings; r += blockDim.x) {
@@ -253,12 +252,6 @@ k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ s
     ri.order_path = 0;
     rings[(size_t)scan * max_rings + r] = ri;
     ring_src[(size_t)scan * max_rings + r] = make_uint2(0u, 0u);  // addressed through the bucketed index list
-  }
-  if (threadIdx.x == 0 && s_n_present) {
-    uint32_t k = s_work_base;
-    for (int r = 0; r < max_rings; r++) {
-      if (s_cnt[r]) { work[k++] = make_uint2((uint32_t)scan, (uint32_t)r); }
-    }
   }
 }
 

@@ -314,13 +314,14 @@ class FeatureExtraction:
         """Which path the last batch took: rings on the sector kernel per lane class, scans/rings on the general path."""
         st = N.BatchStats()
         self._check(self._lib.lfx_last_batch_stats(self._h, C.byref(st)))
-        return {"fast_rings": list(st.fast_rings), "general_scans": int(st.general_scans), "general_rings": int(st.general_rings)}
+        return {"fast_rings": list(st.fast_rings), "general_scans": int(st.general_scans), "general_rings": int(st.general_rings),
+                "indexed_rings": list(st.indexed_rings)}
 
     # -- stage timing
     def set_stage_timing(self, enabled: bool):
         self._check(self._lib.lfx_set_stage_timing(self._h, int(enabled)))
 
     def last_stage_ms(self):
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 6)()   # LFX_N_STAGES
         self._check(self._lib.lfx_last_stage_ms(self._h, ms))
         return tuple(ms)

@@ -236,3 +236,87 @@ def test_full_size_batch_properties(oracle):
         out2 = fe.fetch()
     assert np.array_equal(out.labels, out2.labels) and np.array_equal(out.edge_xyz, out2.edge_xyz)
     assert np.array_equal(out.surface_xyz, out2.surface_xyz) and np.array_equal(out.counts, out2.counts)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Indexed sector path: scans that are not regular are bucketed by ring id; every bucket that is a rotated
+# monotone sequence of polar angles runs on the sector kernel through its index list (k_probe_rings +
+# k_extract_sectors<indexed>), everything else on the per-ring kernel.
+
+def dropout_scan(seed, n_rings, width, drop=0.03, **kw):
+    """Firing-order scan with returns removed at random - what the converter's zero-point filter
+    (point_type_converter/convert.py:201) leaves of a real sweep: ragged rings, no fixed ring period."""
+    cloud = regular_scan(seed, n_rings, width, **kw)
+    keep = np.random.default_rng(seed + 1000).random(len(cloud)) >= drop
+    keep[:n_rings] = True
+    return np.ascontiguousarray(cloud[keep])
+
+
+@pytest.mark.parametrize("direction", ["cw", "ccw"])
+@pytest.mark.parametrize("width", [100, 299, 640, 1024, 1800, 2048, 2232])
+def test_dropout_scans_take_the_indexed_sector_path(oracle, width, direction):
+    clouds = [dropout_scan(width + s, len(adv.KINDS), width, kinds=adv.KINDS, direction=direction) for s in range(3)]
+    for hp in (_hp(), _hp(padding=2, neighbor_degree_threshold=3.0, edge_threshold=50.0, max_range=1000.0),
+               _hp(surface_threshold=1e9, edge_threshold=1e-9)):
+        out, stats = _check(oracle, hp, clouds)
+        assert stats["general_scans"] == 3 and sum(stats["fast_rings"]) == 0, (width, stats)
+        assert sum(stats["indexed_rings"]) == 3 * len(adv.KINDS) and stats["general_rings"] == 0, (width, stats)
+        assert (out.rings["order_path"] == 0).all()
+        _, stats2 = _check(oracle, hp, clouds, diag=False)   # the production instantiation
+        assert stats2 == stats
+
+
+def test_synthetic_tunnel_scans_take_the_indexed_sector_path(oracle):
+    from lidar_feature_extraction_b200 import synth
+
+    sp = synth.spec("hdl64")   # 1 % drop-outs: ragged rings
+    clouds = [synth.scan_host(sp, f) for f in range(4)]
+    for hp in (_hp(), _hp(padding=2, neighbor_degree_threshold=3.0, edge_threshold=50.0, max_range=1000.0)):
+        out, stats = _check(oracle, hp, clouds)
+        assert stats["general_scans"] == 4 and sum(stats["indexed_rings"]) == 4 * sp.n_rings and stats["general_rings"] == 0, stats
+
+
+def test_indexed_rings_that_fail_a_check_are_redone_per_ring(oracle):
+    """Corruptions of single rings of a drop-out scan: only the damaged ring goes to the per-ring kernel."""
+    hp = _hp()
+    n_rings, width = 6, 900
+    good = dropout_scan(1, n_rings, width)
+    ring = good.view(np.uint16).reshape(-1, 16)[:, 10]
+    cases = {}
+    for name, target in (("swap", 1), ("duplicate", 3), ("zero_pair", 5)):
+        c = good.copy()
+        p = _points(c)
+        members = np.nonzero(ring == target)[0]
+        i, j = members[300], members[310]
+        if name == "swap":
+            p[[i, j], 0:3] = p[[j, i], 0:3]
+        elif name == "duplicate":
+            p[members[500], 0:2] = p[members[499], 0:2]
+        else:
+            p[members[200], 0:2] = 0.0
+            p[members[201], 0:2] = 0.0
+        cases[name] = c
+    for name, cloud in cases.items():
+        out, stats = _check(oracle, hp, [good, cloud, good])
+        assert stats["general_scans"] == 3, (name, stats)
+        assert stats["general_rings"] == 1 and sum(stats["indexed_rings"]) == 3 * n_rings, (name, stats)
+    out, _ = _check(oracle, hp, [cases["zero_pair"]])
+    from lidar_feature_extraction_b200 import _native as N
+
+    assert out.rings["status"][0][5] == N.LFX_RING_SKIPPED and out.rings["status"][0][4] == N.LFX_RING_OK
+
+
+def test_indexed_path_mixed_ring_lengths_and_sparse_rings(oracle):
+    """Buckets of very different lengths in one scan (each its own sector table and window class), short and
+    sparse rings next to them, ring-major and shuffled layouts."""
+    lengths = [2232, 64, 300, 17, 1800, 3, 2048, 640, 63, 1024]
+    for shuffle, want_indexed in (("interleave", True), ("rotate", True), ("rotate_reverse", True), ("random", False)):
+        clouds = [adv.ragged_scan(7 + s, lengths, shuffle=shuffle) for s in range(2)]
+        # seven rings have at least 64 points; with 4 sectors the three longest exceed the 384-position window
+        for hp, n_idx in ((_hp(), 7), (_hp(padding=2, n_blocks=4), 4)):
+            out, stats = _check(oracle, hp, clouds)
+            assert stats["general_scans"] == 2, (shuffle, stats)
+            if want_indexed:
+                assert sum(stats["indexed_rings"]) == 2 * n_idx and stats["general_rings"] == 2 * (10 - n_idx), (shuffle, stats)
+            else:
+                assert stats["general_rings"] >= 2 * 3, (shuffle, stats)
