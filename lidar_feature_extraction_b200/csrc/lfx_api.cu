@@ -78,7 +78,9 @@ struct lfx_handle
   DevBuf<uint2> d_ring_featoff;
   DevBuf<uint2> d_ring_src;
   DevBuf<uint32_t> d_scan_flags;
-  DevBuf<uint32_t> d_gen_scan, d_gen_tile_base;
+  DevBuf<uint32_t> d_gen_scan, d_gen_tile_base, d_tile_owner;
+  bool scatter_bm = false;   // bitmap scatter (max_rings small enough for shared memory)
+  int scatter_bm_grid = 0;
   DevBuf<FastRing> d_fast[2 * N_FAST_K];
   DevBuf<SectorRec> d_rec[2 * N_FAST_K];
   DevBuf<int> d_bndx[N_FAST_K];
@@ -279,14 +281,22 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   }
   if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
   // ---- general path for the scans flagged by the probe or by a failed check of the sector kernel
-  k_general_list<<<1, 1024, 0, h->stream>>>(h->d_scans.p, n_scans, h->d_scan_flags.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_counters);
+  k_general_list<<<1, 1024, 0, h->stream>>>(h->d_scans.p, n_scans, h->d_scan_flags.p, h->d_gen_scan.p, h->d_gen_tile_base.p,
+                                            h->d_tile_owner.p, h->d_counters);
   const int ingest_grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_tiles, 1u), (uint32_t)h->ingest_grid);
   k_ring_hist<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
-    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
+    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
   k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
     h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, max_rings, h->params.padding, h->cap);
-  k_ring_scatter<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
-    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
+  if (h->scatter_bm) {
+    const int grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_tiles, 1u), (uint32_t)h->scatter_bm_grid);
+    k_ring_scatter_bm<<<grid, INGEST_THREADS, scatter_bm_smem(max_rings), h->stream>>>(
+      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p,
+      h->d_rings.p, h->d_idx.p, max_rings);
+  } else {
+    k_ring_scatter<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
+      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
+  }
   // ---- bucketed rings that are rotated monotone sequences: sector kernel through the index list; the rest
   //      (and every ring whose hypothesis fails there) form the work list of the per-ring kernel
   RingProbeArgs rp;
@@ -484,6 +494,14 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
     if ((e = cudaFuncSetAttribute(k_ring_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter)"); }
   }
   int occ = 0;
+  // bitmap scatter: 390 B of shared memory per ring id; above ~500 ring ids the match-based scatter takes over
+  h->scatter_bm = h->opt.max_rings % 4 == 0 && scatter_bm_smem(h->opt.max_rings) <= (size_t)prop.sharedMemPerBlockOptin;
+  if (h->scatter_bm) {
+    const size_t sb = scatter_bm_smem(h->opt.max_rings);
+    if ((e = cudaFuncSetAttribute(k_ring_scatter_bm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter_bm)"); }
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ring_scatter_bm, INGEST_THREADS, sb)) != cudaSuccess) { return bail(e, "occupancy(scatter_bm)"); }
+    h->scatter_bm_grid = h->num_sms * std::max(occ, 1);
+  }
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->ring_kernel, h->ring_threads, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
   h->ring_grid = h->num_sms * std::max(occ, 1);
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_copy, 256, 0)) != cudaSuccess) { return bail(e, "occupancy(pack)"); }
@@ -531,7 +549,7 @@ void lfx_destroy(lfx_handle * h)
   cudaFree(h->d_rings.p); cudaFree(h->d_work.p); cudaFree(h->d_ring_featoff.p); cudaFree(h->d_ring_src.p); cudaFree(h->d_scan_flags.p); cudaFree(h->d_idx.p);
   cudaFree(h->d_labels.p); cudaFree(h->d_sorted_src.p); cudaFree(h->d_curv.p); cudaFree(h->d_stage.p);
   cudaFree(h->d_edge.p); cudaFree(h->d_surface.p); cudaFree(h->d_counts.p); cudaFree(h->d_offsets.p);
-  cudaFree(h->d_input.p); cudaFree(h->d_counters); cudaFree(h->d_gen_scan.p); cudaFree(h->d_gen_tile_base.p);
+  cudaFree(h->d_input.p); cudaFree(h->d_counters); cudaFree(h->d_gen_scan.p); cudaFree(h->d_gen_tile_base.p); cudaFree(h->d_tile_owner.p);
   for (int c = 0; c < 2 * N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
   for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_bndx[c].p); }
   cudaFree(h->d_ring_path.p);
@@ -601,6 +619,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
   if ((rc = ensure(h, h->d_scan_flags, ns, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_gen_scan, ns, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_gen_tile_base, ns + 1, &regrown))) { return rc; }
+  if ((rc = ensure(h, h->d_tile_owner, std::max<uint64_t>(total_tiles, 1), &regrown))) { return rc; }
   if (h->fast_enabled) {
     // a regular scan contributes at most min(n_points / FAST_MIN_RING, max_rings) rings to one list
     size_t fast_cap = 0;

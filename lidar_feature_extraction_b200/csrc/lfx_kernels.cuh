@@ -147,7 +147,8 @@ __device__ __forceinline__ int find_gen_scan(const uint32_t * gen_tile_base, int
 // single CTA: list of flagged scans + exclusive prefix of their tile counts
 __global__ void __launch_bounds__(1024)
 k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t * __restrict__ scan_flags,
-               uint32_t * __restrict__ gen_scan, uint32_t * __restrict__ gen_tile_base, uint32_t * counters)
+               uint32_t * __restrict__ gen_scan, uint32_t * __restrict__ gen_tile_base, uint32_t * __restrict__ tile_owner,
+               uint32_t * counters)
 {
   __shared__ uint32_t s_c[1024], s_t[1024];
   const int tid = threadIdx.x;
@@ -166,9 +167,10 @@ k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t 
       __syncthreads();
     }
     if (f) {
-      const uint32_t k = carry_c + s_c[tid] - 1;
+      const uint32_t k = carry_c + s_c[tid] - 1, tb = carry_t + s_t[tid] - nt;
       gen_scan[k] = (uint32_t)i;
-      gen_tile_base[k] = carry_t + s_t[tid] - nt;
+      gen_tile_base[k] = tb;
+      for (uint32_t j = 0; j < nt; j++) { tile_owner[tb + j] = k; }   // general tile -> its entry of gen_scan
     }
     carry_c += s_c[1023]; carry_t += s_t[1023];
     __syncthreads();
@@ -178,18 +180,17 @@ k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t 
 
 __global__ void __launch_bounds__(INGEST_THREADS)
 k_ring_hist(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
-            const uint32_t * __restrict__ gen_tile_base, uint16_t * __restrict__ ring16,
+            const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner, uint16_t * __restrict__ ring16,
             uint32_t * __restrict__ tile_hist, int max_rings, uint32_t * counters)
 {
   extern __shared__ uint32_t s_hist[];
   __shared__ int s_scan;
   __shared__ uint32_t s_tile;
   const uint32_t n_tiles = counters[C_GEN_TILES];
-  const int n_gen = (int)counters[C_GEN_SCANS];
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     __syncthreads();
     if (threadIdx.x == 0) {
-      const int k = find_gen_scan(gen_tile_base, n_gen, t);
+      const uint32_t k = tile_owner[t];
       s_scan = (int)gen_scan[k];
       s_tile = scans[s_scan].tile_base + (t - gen_tile_base[k]);
     }
@@ -318,6 +319,99 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
       }
       __syncwarp();
     }
+  }
+}
+
+// ------------------------------------------------------------------ ingest: stable scatter through ring bitmaps
+//
+// The same stable scatter without warp match operations (a warp of 32 consecutive points in firing order holds
+// 32 distinct ring ids, the slowest case of match.any) and without a serial chain per tile: every point sets
+// its bit in the bitmap of its ring (shared memory, word-major so that a warp's 32 rings hit 32 banks); the
+// rank of a point inside its ring's run of this tile is the number of set bits before it.
+constexpr int BM_WORDS = TILE / 32;
+
+__host__ __device__ inline size_t scatter_bm_smem(int max_rings)
+{
+  return (size_t)max_rings * BM_WORDS * 4 + (size_t)max_rings * BM_WORDS * 2 + (size_t)max_rings * 4;
+}
+
+struct TileJob { uint32_t scan, tile, first, n_points; uint64_t point_base; };
+
+__device__ __forceinline__ TileJob load_tile_job(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
+                                                 const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner, uint32_t t)
+{
+  const uint32_t k = tile_owner[t];
+  TileJob j;
+  j.scan = gen_scan[k];
+  const uint32_t in_scan = t - gen_tile_base[k];
+  const ScanDesc & sd = scans[j.scan];
+  j.tile = sd.tile_base + in_scan;
+  j.first = in_scan * TILE;
+  j.n_points = sd.n_points;
+  j.point_base = sd.point_base;
+  return j;
+}
+
+__global__ void __launch_bounds__(INGEST_THREADS)
+k_ring_scatter_bm(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
+                  const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner,
+                  const uint32_t * __restrict__ counters, const uint16_t * __restrict__ ring16,
+                  const uint32_t * __restrict__ tile_hist, const lfx_ring_info * __restrict__ rings,
+                  uint32_t * __restrict__ idx, int max_rings)
+{
+  extern __shared__ __align__(16) unsigned char bm_raw[];
+  const int R = max_rings;
+  uint32_t * bm = reinterpret_cast<uint32_t *>(bm_raw);               // [BM_WORDS][R]
+  uint16_t * pre = reinterpret_cast<uint16_t *>(bm + (size_t)R * BM_WORDS);   // [BM_WORDS][R] set bits in earlier words
+  uint32_t * rbase = reinterpret_cast<uint32_t *>(pre + (size_t)R * BM_WORDS); // [R] bucket position of the ring's run
+  constexpr int PER = TILE / INGEST_THREADS;   // 8 points per thread: i = c * 256 + tid
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t n_tiles = counters[C_GEN_TILES];
+  uint32_t t = blockIdx.x;
+  if (t >= n_tiles) { return; }
+  TileJob cur = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, t);
+  for (; t < n_tiles; t += gridDim.x) {
+    // the next tile's descriptor chain (three dependent loads) runs while this tile is processed
+    const uint32_t tn = t + gridDim.x < n_tiles ? t + gridDim.x : t;
+    const TileJob nxt = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, tn);
+    uint32_t rg[PER];
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      const uint32_t i = cur.first + c * INGEST_THREADS + tid;
+      rg[c] = i < cur.n_points ? (uint32_t)ring16[cur.point_base + i] : 0xFFFFFFFFu;
+    }
+    __syncthreads();   // the previous tile's bitmaps are no longer read
+    for (int r = tid; r < R; r += INGEST_THREADS) {
+      rbase[r] = rings[(size_t)cur.scan * R + r].offset + tile_hist[(size_t)cur.tile * R + r];
+    }
+    {
+      uint4 * z = reinterpret_cast<uint4 *>(bm);
+      for (int k = tid; k < R * BM_WORDS / 4; k += INGEST_THREADS) { z[k] = make_uint4(0u, 0u, 0u, 0u); }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      if (rg[c] != 0xFFFFFFFFu) { atomicOr(&bm[(c * (INGEST_THREADS / 32) + (tid >> 5)) * R + rg[c]], 1u << lane); }
+    }
+    __syncthreads();
+    for (int r = tid; r < R; r += INGEST_THREADS) {
+      uint32_t run = 0;
+#pragma unroll 8
+      for (int w = 0; w < BM_WORDS; w++) {
+        pre[w * R + r] = (uint16_t)run;
+        run += __popc(bm[w * R + r]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      if (rg[c] != 0xFFFFFFFFu) {
+        const int w = c * (INGEST_THREADS / 32) + (tid >> 5);
+        const uint32_t rank = pre[w * R + rg[c]] + __popc(bm[w * R + rg[c]] & ((1u << lane) - 1u));
+        idx[cur.point_base + rbase[rg[c]] + rank] = cur.first + c * INGEST_THREADS + tid;
+      }
+    }
+    cur = nxt;
   }
 }
 

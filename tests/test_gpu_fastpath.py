@@ -320,3 +320,12 @@ def test_indexed_path_mixed_ring_lengths_and_sparse_rings(oracle):
                 assert sum(stats["indexed_rings"]) == 2 * n_idx and stats["general_rings"] == 2 * (10 - n_idx), (shuffle, stats)
             else:
                 assert stats["general_rings"] >= 2 * 3, (shuffle, stats)
+
+
+@pytest.mark.parametrize("max_rings", [8, 128, 1024])
+def test_bucketing_kernels_for_small_and_large_ring_id_spaces(oracle, max_rings):
+    """max_rings <= ~500 buckets with the bitmap scatter, larger id spaces with the match-based scatter."""
+    ids = [5, 0, 7, 3] if max_rings == 8 else ([100, 3, 64, 127] if max_rings == 128 else [1000, 3, 512, 700])
+    clouds = [dropout_scan(40 + s, 4, 777, ring_ids=ids) for s in range(3)] + [adv.ragged_scan(9, [300, 70, 1500, 20], shuffle="random", ring_ids=ids)]
+    out, stats = _check(oracle, _hp(), clouds, max_rings=max_rings)
+    assert stats["general_scans"] == 4 and sum(stats["indexed_rings"]) >= 12, stats
