@@ -48,28 +48,85 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle-reason sampler running during the timed region."""
+    """SM clock / throttle-reason sampler running DURING the timed region: an NVML polling thread (5 ms
+    period, so that even a 40 ms timed region yields several samples under load); falls back to an
+    `nvidia-smi -lms` child process when NVML is unusable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+            "hw_power_brake_slowdown": 0x80}
 
-    def __init__(self, gpu_index: int):
-        self.path = tempfile.mktemp(prefix="lfx_clocks_", suffix=".csv")
-        self.proc = None
+    def __init__(self, gpu_index: int, uuid: str | None = None, period_s: float = 0.005):
         self.gpu = gpu_index
+        self.uuid = uuid
+        self.period = period_s
+        self.nvml = None
+        self.handle = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.sm, self.reason_bits, self.mx = [], 0, None
+        self.proc = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            if uuid:
+                try:
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if isinstance(uuid, bytes) else uuid.encode())
+                except Exception:
+                    self.handle = None
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._poll()   # first call pays NVML's lazy initialisation outside the timed region
+            self.sm, self.reason_bits = [], 0
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.reason_bits |= int(get(self.handle))
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._poll()
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.path = tempfile.mktemp(prefix="lfx_clocks_", suffix=".csv")
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self) -> dict:
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["unsampled"]}
+            reasons = sorted(k for k, b in self.BITS.items() if self.reason_bits & b)
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": reasons,
+                    "samples": len(self.sm), "sm_min_mhz": float(min(self.sm)), "source": "nvml, 5 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -96,7 +153,8 @@ class ClockSampler:
             pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 20"}
 
 
 def host_cores() -> int:
@@ -257,7 +315,11 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
