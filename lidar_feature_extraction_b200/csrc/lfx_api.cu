@@ -276,7 +276,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       sa.max_rings = max_rings;
       sa.inv_blocks = (uint32_t)(0x100000000ull / (uint64_t)h->params.n_blocks);
       sa.prm = h->dev;
-      h->sector_kernel[c]<<<h->sector_grid[c], sector_warps(fast_k(c)) * 32, h->sector_smem[c], h->stream>>>(sa);
+      h->sector_kernel[c]<<<h->sector_grid[c], sector_warps(fast_k(c), false) * 32, h->sector_smem[c], h->stream>>>(sa);
     }
   }
   if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
@@ -333,7 +333,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       sa.max_rings = max_rings;
       sa.inv_blocks = (uint32_t)(0x100000000ull / (uint64_t)h->params.n_blocks);
       sa.prm = h->dev;
-      h->sector_kernel[N_FAST_K + c]<<<h->sector_grid[N_FAST_K + c], sector_warps(fast_k(c)) * 32, h->sector_smem[N_FAST_K + c], h->stream>>>(sa);
+      h->sector_kernel[N_FAST_K + c]<<<h->sector_grid[N_FAST_K + c], sector_warps(fast_k(c), true) * 32, h->sector_smem[N_FAST_K + c], h->stream>>>(sa);
     }
   }
   if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[4], h->stream)); }
@@ -511,15 +511,15 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->fast_enabled = h->opt.force_order_path == 0 && params->n_blocks <= FAST_MAX_BLOCKS &&
                     pick_sector_kernels(params->padding, h->opt.want_sorted_src || h->opt.want_curvature, h->sector_kernel);
   if (h->fast_enabled) {
-    h->sector_smem[0] = sector_smem_bytes<fast_k(0), false>(sector_warps(fast_k(0)));
-    h->sector_smem[1] = sector_smem_bytes<fast_k(1), false>(sector_warps(fast_k(1)));
-    h->sector_smem[2] = sector_smem_bytes<fast_k(2), false>(sector_warps(fast_k(2)));
-    h->sector_smem[3] = sector_smem_bytes<fast_k(0), true>(sector_warps(fast_k(0)));
-    h->sector_smem[4] = sector_smem_bytes<fast_k(1), true>(sector_warps(fast_k(1)));
-    h->sector_smem[5] = sector_smem_bytes<fast_k(2), true>(sector_warps(fast_k(2)));
+    h->sector_smem[0] = sector_smem_bytes<fast_k(0), false>(sector_warps(fast_k(0), false));
+    h->sector_smem[1] = sector_smem_bytes<fast_k(1), false>(sector_warps(fast_k(1), false));
+    h->sector_smem[2] = sector_smem_bytes<fast_k(2), false>(sector_warps(fast_k(2), false));
+    h->sector_smem[3] = sector_smem_bytes<fast_k(0), true>(sector_warps(fast_k(0), true));
+    h->sector_smem[4] = sector_smem_bytes<fast_k(1), true>(sector_warps(fast_k(1), true));
+    h->sector_smem[5] = sector_smem_bytes<fast_k(2), true>(sector_warps(fast_k(2), true));
     for (int c = 0; c < 2 * N_FAST_K; c++) {
       if ((e = cudaFuncSetAttribute(h->sector_kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sector_smem[c])) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(sectors)"); }
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c % N_FAST_K)) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c % N_FAST_K), c >= N_FAST_K) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
       if (occ < 1) { g_create_error = "sector kernel does not fit on this device"; lfx_destroy(h); return LFX_E_CUDA; }
       h->sector_grid[c] = h->num_sms * occ;
     }
