@@ -36,7 +36,9 @@ enum {
   LFX_E_BAD_LAYOUT = 4, /* PointCloud2 view that pcl::fromROSMsg could not map either */
   LFX_E_CAPACITY = 5,   /* a ring longer than max_ring_points / ring id >= max_rings (see lfx_options) */
   LFX_E_CUDA = 6,
-  LFX_E_STATE = 7       /* call order violated (e.g. fetch before extract) */
+  LFX_E_STATE = 7,      /* call order violated (e.g. fetch before extract) */
+  LFX_E_CONVERT = 8     /* lfx_convert_batch: at least one cloud failed where the reference converter raises;
+                           per-cloud reasons in lfx_convert_result.status */
 };
 
 /* ------------------------------------------------------------------ labels
@@ -199,6 +201,64 @@ int lfx_extract_scan(lfx_handle *h, const lfx_cloud_view *scan, lfx_scan_output 
 /* LabelToColor, extraction/src/color_points.cpp:39-68 (colored_scan is derived on the host from
  * the label bytes; it is a depth-1 debug topic, feature_extraction.cpp:77-78). rgb[3]. */
 int lfx_label_to_color(uint8_t label, uint8_t *rgb);
+
+/* ------------------------------------------------------------------ upstream converter
+ * Replaces PointTypeConverter.callback (point_type_converter/point_type_converter/convert.py:183-212): a raw
+ * driver PointCloud2 - any field set, any sensor_msgs/PointField datatype, either byte order - becomes the
+ * deployed 32-byte layout (make_fields, convert.py:137-145: x,y,z,padding,intensity f32 @0..19, ring u16 @20,
+ * bytes 22..31 zero, little-endian, is_dense) with the all-zero returns removed (nonzero, convert.py:165-166),
+ * in the input's point order. The reference's struct-format behaviour is kept to the letter: a FLOAT32 field
+ * 'padding' at offset 12 is appended, fields are read in offset order at their effective offsets
+ * (create_point_format, convert.py:69-81), the zero test looks at the first three fields in offset order, and
+ * the fields named x, y, z, padding, intensity, ring are packed positionally into '<fffffH'. */
+typedef struct lfx_point_field {   /* sensor_msgs/PointField */
+  const char *name;
+  uint32_t offset;
+  uint8_t datatype;                /* 1 INT8, 2 UINT8, 3 INT16, 4 UINT16, 5 INT32, 6 UINT32, 7 FLOAT32, 8 FLOAT64 */
+  uint32_t count;                  /* ignored, as in the reference (one value per field) */
+} lfx_point_field;
+
+typedef struct lfx_raw_cloud {     /* the parts of sensor_msgs/PointCloud2 the converter reads */
+  const void *data;
+  uint64_t data_bytes;             /* must be a multiple of point_step (convert.py:91-92) */
+  uint32_t point_step;
+  const lfx_point_field *fields;
+  uint32_t n_fields;
+  uint8_t is_bigendian;
+  uint8_t memory;                  /* LFX_MEM_HOST or LFX_MEM_DEVICE */
+} lfx_raw_cloud;
+
+/* per-cloud outcome: where the reference's callback raises, and why */
+enum {
+  LFX_CONVERT_OK = 0,
+  LFX_CONVERT_E_SIZE = 1,          /* data size is not a multiple of point_step (convert.py:91-92) */
+  LFX_CONVERT_E_DATATYPE = 2,      /* datatype id outside 1..8 (KeyError in create_point_format) */
+  LFX_CONVERT_E_LAYOUT = 3,        /* fields run past point_step: struct.unpack size mismatch (convert.py:90-97) */
+  LFX_CONVERT_E_FEW_FIELDS = 4,    /* fewer than three fields: nonzero() indexes c[0..2] (convert.py:165-166) */
+  LFX_CONVERT_E_FIELD_COUNT = 5,   /* kept points do not carry exactly six retained values (struct.pack) */
+  LFX_CONVERT_E_OVERFLOW = 6,      /* a finite value does not fit the 'f' format */
+  LFX_CONVERT_E_RING_TYPE = 7,     /* the sixth retained field is a float: 'H' needs an integer */
+  LFX_CONVERT_E_RING_RANGE = 8     /* 'H' format requires 0 <= ring <= 65535 */
+};
+
+/* Result of the last lfx_convert_batch. Arrays are host memory owned by the handle; d_points is device memory.
+ * Cloud c owns kept[c] converted points at d_points + 32 * point_base[c] (point_base is the prefix sum of the
+ * INPUT point counts, so every cloud has room for all of its points). Valid until the next lfx_convert_batch. */
+typedef struct lfx_convert_result {
+  int n_clouds;
+  const uint8_t *d_points;
+  const uint64_t *point_base;      /* [n_clouds + 1] */
+  const uint32_t *kept;            /* [n_clouds] = width of the converted cloud (0 for failed clouds) */
+  const uint32_t *status;          /* [n_clouds] LFX_CONVERT_* */
+} lfx_convert_result;
+
+/* Converts n_clouds independent clouds in one launch. Synchronous (the caller needs the widths). Returns LFX_OK,
+ * or LFX_E_CONVERT when at least one cloud failed (the others are converted). */
+int lfx_convert_batch(lfx_handle *h, const lfx_raw_cloud *clouds, int n_clouds, lfx_convert_result *out);
+/* View of converted cloud `cloud` (device memory, deployed layout) ready for lfx_extract_batch. */
+int lfx_converted_view(lfx_handle *h, int cloud, lfx_cloud_view *out);
+/* Copies converted cloud `cloud` (32 * kept bytes = PointCloud2.data of /points_converted) to host memory. */
+int lfx_fetch_converted(lfx_handle *h, int cloud, void *dst, size_t capacity_bytes);
 
 /* ------------------------------------------------------------------ memory helpers */
 /* Pinned host memory so that H2D/D2H run at full PCIe speed. */

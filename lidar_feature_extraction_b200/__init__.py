@@ -16,9 +16,10 @@ from .extraction import (  # noqa: F401
     label_to_color,
     launch_yaml_params,
 )
+from .converter import ConvertError, PointTypeConverter  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = [
     "FeatureExtraction", "HyperParameters", "PointCloud2", "PointField", "ExtractionError", "default_params",
-    "launch_yaml_params", "label_to_color", "synth", "POINT_STEP",
+    "launch_yaml_params", "label_to_color", "synth", "POINT_STEP", "PointTypeConverter", "ConvertError",
 ]

@@ -15,9 +15,13 @@ ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.environ.get("LFX_LIB") or os.path.join(PKG_DIR, "liblfx.so")  # LFX_LIB: A/B builds of the same ABI
 HEADER = os.path.join(ROOT, "include", "lfx.h")
 
-LFX_OK, LFX_E_BAD_PARAM, LFX_E_NOT_DENSE, LFX_E_NO_RING, LFX_E_BAD_LAYOUT, LFX_E_CAPACITY, LFX_E_CUDA, LFX_E_STATE = range(8)
+(LFX_OK, LFX_E_BAD_PARAM, LFX_E_NOT_DENSE, LFX_E_NO_RING, LFX_E_BAD_LAYOUT, LFX_E_CAPACITY, LFX_E_CUDA, LFX_E_STATE,
+ LFX_E_CONVERT) = range(9)
 STATUS_NAMES = ["LFX_OK", "LFX_E_BAD_PARAM", "LFX_E_NOT_DENSE", "LFX_E_NO_RING", "LFX_E_BAD_LAYOUT", "LFX_E_CAPACITY",
-                "LFX_E_CUDA", "LFX_E_STATE"]
+                "LFX_E_CUDA", "LFX_E_STATE", "LFX_E_CONVERT"]
+CONVERT_STATUS_NAMES = ["LFX_CONVERT_OK", "LFX_CONVERT_E_SIZE", "LFX_CONVERT_E_DATATYPE", "LFX_CONVERT_E_LAYOUT",
+                        "LFX_CONVERT_E_FEW_FIELDS", "LFX_CONVERT_E_FIELD_COUNT", "LFX_CONVERT_E_OVERFLOW",
+                        "LFX_CONVERT_E_RING_TYPE", "LFX_CONVERT_E_RING_RANGE"]
 LFX_MEM_HOST, LFX_MEM_DEVICE = 0, 1
 LFX_RING_U8, LFX_RING_U16, LFX_RING_U32 = 2, 4, 6
 LFX_RING_OK, LFX_RING_SPARSE, LFX_RING_SKIPPED, LFX_RING_TOO_LONG = range(4)
@@ -114,6 +118,23 @@ class BatchStats(C.Structure):
                 ("indexed_rings", C.c_uint32 * 3)]
 
 
+class PointFieldC(C.Structure):
+    """lfx_point_field == sensor_msgs/PointField."""
+
+    _fields_ = [("name", C.c_char_p), ("offset", C.c_uint32), ("datatype", C.c_uint8), ("count", C.c_uint32)]
+
+
+class RawCloud(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_bytes", C.c_uint64), ("point_step", C.c_uint32),
+                ("fields", C.POINTER(PointFieldC)), ("n_fields", C.c_uint32), ("is_bigendian", C.c_uint8),
+                ("memory", C.c_uint8)]
+
+
+class ConvertResult(C.Structure):
+    _fields_ = [("n_clouds", C.c_int), ("d_points", C.c_void_p), ("point_base", C.POINTER(C.c_uint64)),
+                ("kept", C.POINTER(C.c_uint32)), ("status", C.POINTER(C.c_uint32))]
+
+
 class SynthSpec(C.Structure):
     _fields_ = [
         ("n_rings", C.c_int),
@@ -191,6 +212,9 @@ def lib() -> C.CDLL:
     L.lfx_set_stage_timing.argtypes = [H, C.c_int]
     L.lfx_last_stage_ms.argtypes = [H, C.c_void_p]
     L.lfx_last_batch_stats.argtypes = [H, C.POINTER(BatchStats)]
+    L.lfx_convert_batch.argtypes = [H, C.POINTER(RawCloud), C.c_int, C.POINTER(ConvertResult)]
+    L.lfx_converted_view.argtypes = [H, C.c_int, C.POINTER(CloudView)]
+    L.lfx_fetch_converted.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]
     L.lfx_synth_scan_host.argtypes = [C.POINTER(SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
     L.lfx_synth_batch_device.argtypes = [H, C.POINTER(SynthSpec), C.c_uint64, C.c_int, C.c_void_p]

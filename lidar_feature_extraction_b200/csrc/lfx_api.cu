@@ -22,6 +22,7 @@
 #include "lfx_ring.cuh"
 #include "lfx_sector.cuh"
 #include "lfx_synth.h"
+#include "lfx_convert.cuh"
 
 using namespace lfxk;
 
@@ -93,6 +94,14 @@ struct lfx_handle
   DevBuf<uint32_t> d_counts, d_offsets;
   DevBuf<uint8_t> d_input;
   uint32_t * d_counters = nullptr;
+  // upstream converter (lfx_convert_batch)
+  DevBuf<uint8_t> d_conv_raw, d_conv_out;
+  DevBuf<ConvCloud> d_conv_clouds;
+  DevBuf<unsigned long long> d_conv_state;
+  DevBuf<uint32_t> d_conv_meta;     // ticket | kept[n] | flags[n]
+  std::vector<uint64_t> conv_point_base;
+  std::vector<uint32_t> conv_kept, conv_status;
+  bool have_conv = false;
 
   // pinned host staging
   ScanDesc * h_scans = nullptr;
@@ -553,6 +562,7 @@ void lfx_destroy(lfx_handle * h)
   for (int c = 0; c < 2 * N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
   for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_bndx[c].p); }
   cudaFree(h->d_ring_path.p);
+  cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p);
   cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
   for (auto & ev : h->ev) { if (ev) { cudaEventDestroy(ev); } }
@@ -1036,3 +1046,208 @@ extern "C" int lfx_synth_batch_device(lfx_handle * h, const lfx_synth_spec * spe
   h->launches += 1;
   return LFX_OK;
 }
+
+// ---------------------------------------------------------------- upstream converter
+
+namespace
+{
+
+struct ConvField { std::string name; uint32_t offset; uint32_t dt; };
+
+int conv_dt_size(uint32_t dt) { return dt <= 2 ? 1 : (dt <= 4 ? 2 : (dt <= 7 ? 4 : 8)); }
+
+// Host half of PointTypeConverter.callback: convert.py:184-186 (append 'padding', stable sort by offset),
+// create_point_format (convert.py:69-81: effective offsets never step backwards; the per-point format is
+// max(end of last field, point_step) bytes long) and find_indices (convert.py:118-119). Returns LFX_CONVERT_*;
+// `needs_six` reports that kept points could not be packed (decided once the kept count is known).
+uint32_t conv_make_plan(const lfx_raw_cloud & rc, ConvCloud & cc, bool & needs_six, bool & ring_float)
+{
+  needs_six = false;
+  ring_float = false;
+  std::vector<ConvField> fs;
+  for (uint32_t i = 0; i < rc.n_fields; i++) { fs.push_back({rc.fields[i].name ? rc.fields[i].name : "", rc.fields[i].offset, rc.fields[i].datatype}); }
+  fs.push_back({"padding", 12u, 7u});
+  std::stable_sort(fs.begin(), fs.end(), [](const ConvField & a, const ConvField & b) { return a.offset < b.offset; });
+  std::vector<uint64_t> eff(fs.size());
+  uint64_t index = 0;
+  for (size_t i = 0; i < fs.size(); i++) {
+    if (fs[i].dt < 1 || fs[i].dt > 8) { return LFX_CONVERT_E_DATATYPE; }
+    if (index < fs[i].offset) { index = fs[i].offset; }
+    eff[i] = index;
+    index += (uint64_t)conv_dt_size(fs[i].dt);
+  }
+  const uint64_t n = rc.data_bytes / rc.point_step;
+  if (n == 0) { return LFX_CONVERT_OK; }
+  if (std::max<uint64_t>(index, rc.point_step) != rc.point_step) { return LFX_CONVERT_E_LAYOUT; }
+  if (fs.size() < 3) { return LFX_CONVERT_E_FEW_FIELDS; }
+  static const char * const keep_names[] = {"x", "y", "z", "padding", "intensity", "ring"};
+  std::vector<size_t> retained;
+  for (size_t i = 0; i < fs.size(); i++) {
+    for (const char * k : keep_names) { if (fs[i].name == k) { retained.push_back(i); break; } }
+  }
+  const bool aligned_base = reinterpret_cast<uintptr_t>(rc.data) % 16 == 0 || rc.memory == LFX_MEM_HOST;  // host clouds are staged at aligned addresses
+  auto put = [&](int slot, size_t i) {
+    cc.off[slot] = (uint16_t)eff[i];
+    cc.dt[slot] = (uint8_t)fs[i].dt;
+    const uint64_t size = (uint64_t)conv_dt_size(fs[i].dt);
+    cc.aligned[slot] = (aligned_base && eff[i] % size == 0 && rc.point_step % size == 0) ? 1 : 0;
+  };
+  for (int k = 0; k < 3; k++) { put(k, (size_t)k); }
+  cc.packable = retained.size() == 6 ? 1 : 0;
+  needs_six = !cc.packable;
+  for (int k = 0; k < 6; k++) { put(3 + k, cc.packable ? retained[(size_t)k] : 0); }
+  if (cc.packable && fs[retained[5]].dt >= 7) {   // 'H' wants an integer: the five float slots are still checked first
+    ring_float = true;
+    cc.dt[8] = 2; cc.off[8] = 0; cc.aligned[8] = 0;
+  }
+  return LFX_CONVERT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds, lfx_convert_result * out)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (n_clouds < 0 || (n_clouds > 0 && !clouds)) { return fail(h, LFX_E_BAD_PARAM, "bad clouds argument"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  h->have_conv = false;
+  h->conv_point_base.assign((size_t)n_clouds + 1, 0);
+  h->conv_kept.assign((size_t)n_clouds, 0);
+  h->conv_status.assign((size_t)n_clouds, LFX_CONVERT_OK);
+  std::vector<ConvCloud> cc((size_t)n_clouds);
+  std::vector<uint8_t> needs_six((size_t)n_clouds, 0), ring_float((size_t)n_clouds, 0), active((size_t)n_clouds, 0);
+  uint64_t points = 0, host_bytes = 0;
+  uint32_t tiles = 0, max_step = 16;
+  for (int c = 0; c < n_clouds; c++) {
+    const lfx_raw_cloud & rc = clouds[c];
+    ConvCloud & k = cc[(size_t)c];
+    memset(&k, 0, sizeof(k));
+    h->conv_point_base[(size_t)c] = points;
+    k.tile_base = tiles;
+    if (rc.n_fields > 0 && !rc.fields) { return fail(h, LFX_E_BAD_PARAM, "cloud without a field array"); }
+    if (rc.point_step == 0 || rc.data_bytes % rc.point_step != 0) { h->conv_status[(size_t)c] = LFX_CONVERT_E_SIZE; continue; }
+    if (rc.point_step > 65535u) { return fail(h, LFX_E_BAD_PARAM, "point_step > 65535 is outside the supported envelope"); }
+    const uint64_t n = rc.data_bytes / rc.point_step;
+    if (n > 0xFFFFFFFFull) { return fail(h, LFX_E_BAD_PARAM, "more than 2^32 - 1 points in one cloud"); }
+    if (n > 0 && !rc.data) { return fail(h, LFX_E_BAD_PARAM, "cloud without data"); }
+    bool six = false, rf = false;
+    const uint32_t st = conv_make_plan(rc, k, six, rf);
+    h->conv_status[(size_t)c] = st;
+    if (st != LFX_CONVERT_OK || n == 0) { continue; }
+    needs_six[(size_t)c] = six; ring_float[(size_t)c] = rf; active[(size_t)c] = 1;
+    k.n_points = (uint32_t)n;
+    k.point_step = rc.point_step;
+    k.big = rc.is_bigendian ? 1 : 0;
+    k.staged = (rc.point_step <= (uint32_t)CONV_STAGE_MAX_STEP && (rc.memory == LFX_MEM_HOST || reinterpret_cast<uintptr_t>(rc.data) % 16 == 0)) ? 1 : 0;
+    if (k.staged) { max_step = std::max(max_step, rc.point_step); }
+    if (rc.memory == LFX_MEM_HOST) { host_bytes = (host_bytes + 255) & ~255ull; host_bytes += rc.data_bytes; }
+    points += n;
+    tiles += (uint32_t)((n + CONV_TILE - 1) / CONV_TILE);
+  }
+  h->conv_point_base[(size_t)n_clouds] = points;
+  int rc_all = LFX_OK;
+  if (tiles > 0) {
+    int rc;
+    if ((rc = ensure(h, h->d_conv_raw, (size_t)host_bytes + 256, nullptr))) { return rc; }
+    if ((rc = ensure(h, h->d_conv_out, (size_t)points * 32 + 32, nullptr))) { return rc; }
+    if ((rc = ensure(h, h->d_conv_clouds, (size_t)n_clouds, nullptr))) { return rc; }
+    if ((rc = ensure(h, h->d_conv_state, (size_t)tiles, nullptr))) { return rc; }
+    if ((rc = ensure(h, h->d_conv_meta, (size_t)1 + 2 * (size_t)n_clouds, nullptr))) { return rc; }
+    uint64_t hb = 0;
+    for (int c = 0; c < n_clouds; c++) {
+      if (!active[(size_t)c]) { continue; }
+      ConvCloud & k = cc[(size_t)c];
+      k.out = h->d_conv_out.p + h->conv_point_base[(size_t)c] * 32;
+      if (clouds[c].memory == LFX_MEM_HOST) {
+        hb = (hb + 255) & ~255ull;
+        LFX_CUDA(h, cudaMemcpyAsync(h->d_conv_raw.p + hb, clouds[c].data, clouds[c].data_bytes, cudaMemcpyHostToDevice, h->stream));
+        k.data = h->d_conv_raw.p + hb;
+        hb += clouds[c].data_bytes;
+      } else {
+        k.data = static_cast<const uint8_t *>(clouds[c].data);
+      }
+    }
+    LFX_CUDA(h, cudaMemcpyAsync(h->d_conv_clouds.p, cc.data(), sizeof(ConvCloud) * (size_t)n_clouds, cudaMemcpyHostToDevice, h->stream));
+    LFX_CUDA(h, cudaMemsetAsync(h->d_conv_state.p, 0, sizeof(unsigned long long) * tiles, h->stream));
+    LFX_CUDA(h, cudaMemsetAsync(h->d_conv_meta.p, 0, sizeof(uint32_t) * (1 + 2 * (size_t)n_clouds), h->stream));
+    ConvArgs a;
+    a.clouds = h->d_conv_clouds.p;
+    a.n_clouds = n_clouds;
+    a.n_tiles = tiles;
+    a.tile_state = h->d_conv_state.p;
+    a.ticket = h->d_conv_meta.p;
+    a.kept = h->d_conv_meta.p + 1;
+    a.flags = h->d_conv_meta.p + 1 + n_clouds;
+    k_convert<<<tiles, CONV_TILE, (size_t)CONV_TILE * max_step, h->stream>>>(a);
+    LFX_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    std::vector<uint32_t> meta((size_t)2 * n_clouds);
+    LFX_CUDA(h, cudaMemcpyAsync(meta.data(), h->d_conv_meta.p + 1, sizeof(uint32_t) * 2 * (size_t)n_clouds, cudaMemcpyDeviceToHost, h->stream));
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < n_clouds; c++) {
+      if (!active[(size_t)c]) { continue; }
+      const uint32_t kept = meta[(size_t)c], fl = meta[(size_t)n_clouds + c];
+      uint32_t st = LFX_CONVERT_OK;
+      if (kept > 0) {   // struct.pack only fails when there is something to pack
+        if (needs_six[(size_t)c]) { st = LFX_CONVERT_E_FIELD_COUNT; }
+        else if (fl & CONV_F_OVERFLOW) { st = LFX_CONVERT_E_OVERFLOW; }
+        else if (ring_float[(size_t)c]) { st = LFX_CONVERT_E_RING_TYPE; }
+        else if (fl & CONV_F_RING_RANGE) { st = LFX_CONVERT_E_RING_RANGE; }
+      }
+      h->conv_status[(size_t)c] = st;
+      h->conv_kept[(size_t)c] = st == LFX_CONVERT_OK ? kept : 0;
+    }
+  }
+  for (int c = 0; c < n_clouds; c++) {
+    if (h->conv_status[(size_t)c] != LFX_CONVERT_OK && rc_all == LFX_OK) {
+      rc_all = fail(h, LFX_E_CONVERT, "cloud " + std::to_string(c) + ": the reference converter raises here (LFX_CONVERT_* = " +
+                                        std::to_string(h->conv_status[(size_t)c]) + ")");
+    }
+  }
+  h->have_conv = true;
+  if (out) {
+    out->n_clouds = n_clouds;
+    out->d_points = h->d_conv_out.p;
+    out->point_base = h->conv_point_base.data();
+    out->kept = h->conv_kept.data();
+    out->status = h->conv_status.data();
+  }
+  return rc_all;
+}
+
+int lfx_converted_view(lfx_handle * h, int cloud, lfx_cloud_view * out)
+{
+  if (!h || !out) { return LFX_E_BAD_PARAM; }
+  if (!h->have_conv) { return fail(h, LFX_E_STATE, "no batch has been converted"); }
+  if (cloud < 0 || (size_t)cloud >= h->conv_kept.size()) { return fail(h, LFX_E_BAD_PARAM, "cloud index out of range"); }
+  if (h->conv_status[(size_t)cloud] != LFX_CONVERT_OK) { return fail(h, LFX_E_CONVERT, "this cloud was not converted"); }
+  memset(out, 0, sizeof(*out));
+  out->data = h->d_conv_out.p ? h->d_conv_out.p + h->conv_point_base[(size_t)cloud] * 32 : nullptr;
+  out->n_points = h->conv_kept[(size_t)cloud];
+  out->point_step = 32;                         // make_fields, convert.py:134-145
+  out->off_x = 0; out->off_y = 4; out->off_z = 8; out->off_ring = 20;
+  out->ring_datatype = LFX_RING_U16;
+  out->has_ring = 1;
+  out->is_dense = 1;                            // convert.py:210
+  out->memory = LFX_MEM_DEVICE;
+  return LFX_OK;
+}
+
+int lfx_fetch_converted(lfx_handle * h, int cloud, void * dst, size_t capacity_bytes)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_conv) { return fail(h, LFX_E_STATE, "no batch has been converted"); }
+  if (cloud < 0 || (size_t)cloud >= h->conv_kept.size()) { return fail(h, LFX_E_BAD_PARAM, "cloud index out of range"); }
+  if (h->conv_status[(size_t)cloud] != LFX_CONVERT_OK) { return fail(h, LFX_E_CONVERT, "this cloud was not converted"); }
+  const size_t bytes = (size_t)h->conv_kept[(size_t)cloud] * 32;
+  if (bytes > capacity_bytes || (bytes > 0 && !dst)) { return fail(h, LFX_E_BAD_PARAM, "destination too small"); }
+  if (bytes == 0) { return LFX_OK; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMemcpyAsync(dst, h->d_conv_out.p + h->conv_point_base[(size_t)cloud] * 32, bytes, cudaMemcpyDeviceToHost, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+}  // extern "C"
