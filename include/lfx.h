@@ -255,6 +255,8 @@ typedef struct lfx_convert_result {
 /* Converts n_clouds independent clouds in one launch. Synchronous (the caller needs the widths). Returns LFX_OK,
  * or LFX_E_CONVERT when at least one cloud failed (the others are converted). */
 int lfx_convert_batch(lfx_handle *h, const lfx_raw_cloud *clouds, int n_clouds, lfx_convert_result *out);
+/* Device time of the last batch's conversion kernel (CUDA events on the handle's stream). */
+int lfx_last_convert_ms(lfx_handle *h, float *ms);
 /* View of converted cloud `cloud` (device memory, deployed layout) ready for lfx_extract_batch. */
 int lfx_converted_view(lfx_handle *h, int cloud, lfx_cloud_view *out);
 /* Copies converted cloud `cloud` (32 * kept bytes = PointCloud2.data of /points_converted) to host memory. */

@@ -213,6 +213,7 @@ def lib() -> C.CDLL:
     L.lfx_last_stage_ms.argtypes = [H, C.c_void_p]
     L.lfx_last_batch_stats.argtypes = [H, C.POINTER(BatchStats)]
     L.lfx_convert_batch.argtypes = [H, C.POINTER(RawCloud), C.c_int, C.POINTER(ConvertResult)]
+    L.lfx_last_convert_ms.argtypes = [H, C.POINTER(C.c_float)]
     L.lfx_converted_view.argtypes = [H, C.c_int, C.POINTER(CloudView)]
     L.lfx_fetch_converted.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]

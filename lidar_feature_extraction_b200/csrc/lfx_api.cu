@@ -99,6 +99,9 @@ struct lfx_handle
   DevBuf<ConvCloud> d_conv_clouds;
   DevBuf<unsigned long long> d_conv_state;
   DevBuf<uint32_t> d_conv_meta;     // ticket | kept[n] | flags[n]
+  DevBuf<uint32_t> d_conv_tile_cloud;
+  cudaEvent_t conv_ev[2] = {nullptr, nullptr};
+  bool conv_smem_set = false;
   std::vector<uint64_t> conv_point_base;
   std::vector<uint32_t> conv_kept, conv_status;
   bool have_conv = false;
@@ -562,7 +565,8 @@ void lfx_destroy(lfx_handle * h)
   for (int c = 0; c < 2 * N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
   for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_bndx[c].p); }
   cudaFree(h->d_ring_path.p);
-  cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p);
+  cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p); cudaFree(h->d_conv_tile_cloud.p);
+  for (auto & ev : h->conv_ev) { if (ev) { cudaEventDestroy(ev); } }
   cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
   for (auto & ev : h->ev) { if (ev) { cudaEventDestroy(ev); } }
@@ -1096,6 +1100,10 @@ uint32_t conv_make_plan(const lfx_raw_cloud & rc, ConvCloud & cc, bool & needs_s
   cc.packable = retained.size() == 6 ? 1 : 0;
   needs_six = !cc.packable;
   for (int k = 0; k < 6; k++) { put(3 + k, cc.packable ? retained[(size_t)k] : 0); }
+  cc.fast = rc.is_bigendian ? 0 : 1;
+  for (int k = 0; k < 8; k++) { if (cc.dt[k] != 7 || !cc.aligned[k]) { cc.fast = 0; } }
+  if (!cc.aligned[8] || !(cc.dt[8] == 2 || cc.dt[8] == 4 || cc.dt[8] == 6)) { cc.fast = 0; }
+  if (!cc.packable) { cc.fast = 0; }
   if (cc.packable && fs[retained[5]].dt >= 7) {   // 'H' wants an integer: the five float slots are still checked first
     ring_float = true;
     cc.dt[8] = 2; cc.off[8] = 0; cc.aligned[8] = 0;
@@ -1118,8 +1126,10 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
   h->conv_status.assign((size_t)n_clouds, LFX_CONVERT_OK);
   std::vector<ConvCloud> cc((size_t)n_clouds);
   std::vector<uint8_t> needs_six((size_t)n_clouds, 0), ring_float((size_t)n_clouds, 0), active((size_t)n_clouds, 0);
+  std::vector<uint32_t> tile_cloud;
+  bool all_fast = true;
   uint64_t points = 0, host_bytes = 0;
-  uint32_t tiles = 0, max_step = 16;
+  uint32_t tiles = 0, max_step = 1;
   for (int c = 0; c < n_clouds; c++) {
     const lfx_raw_cloud & rc = clouds[c];
     ConvCloud & k = cc[(size_t)c];
@@ -1137,14 +1147,17 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
     h->conv_status[(size_t)c] = st;
     if (st != LFX_CONVERT_OK || n == 0) { continue; }
     needs_six[(size_t)c] = six; ring_float[(size_t)c] = rf; active[(size_t)c] = 1;
+    all_fast = all_fast && k.fast;
     k.n_points = (uint32_t)n;
     k.point_step = rc.point_step;
     k.big = rc.is_bigendian ? 1 : 0;
-    k.staged = (rc.point_step <= (uint32_t)CONV_STAGE_MAX_STEP && (rc.memory == LFX_MEM_HOST || reinterpret_cast<uintptr_t>(rc.data) % 16 == 0)) ? 1 : 0;
+    k.staged = ((uint64_t)rc.point_step * CONV_TILE <= (uint64_t)CONV_STAGE_MAX_BYTES && (rc.memory == LFX_MEM_HOST || reinterpret_cast<uintptr_t>(rc.data) % 16 == 0)) ? 1 : 0;
     if (k.staged) { max_step = std::max(max_step, rc.point_step); }
     if (rc.memory == LFX_MEM_HOST) { host_bytes = (host_bytes + 255) & ~255ull; host_bytes += rc.data_bytes; }
     points += n;
-    tiles += (uint32_t)((n + CONV_TILE - 1) / CONV_TILE);
+    const uint32_t nt = (uint32_t)((n + CONV_TILE - 1) / CONV_TILE);
+    tile_cloud.insert(tile_cloud.end(), nt, (uint32_t)c);
+    tiles += nt;
   }
   h->conv_point_base[(size_t)n_clouds] = points;
   int rc_all = LFX_OK;
@@ -1154,6 +1167,7 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
     if ((rc = ensure(h, h->d_conv_out, (size_t)points * 32 + 32, nullptr))) { return rc; }
     if ((rc = ensure(h, h->d_conv_clouds, (size_t)n_clouds, nullptr))) { return rc; }
     if ((rc = ensure(h, h->d_conv_state, (size_t)tiles, nullptr))) { return rc; }
+    if ((rc = ensure(h, h->d_conv_tile_cloud, (size_t)tiles, nullptr))) { return rc; }
     if ((rc = ensure(h, h->d_conv_meta, (size_t)1 + 2 * (size_t)n_clouds, nullptr))) { return rc; }
     uint64_t hb = 0;
     for (int c = 0; c < n_clouds; c++) {
@@ -1170,18 +1184,30 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
       }
     }
     LFX_CUDA(h, cudaMemcpyAsync(h->d_conv_clouds.p, cc.data(), sizeof(ConvCloud) * (size_t)n_clouds, cudaMemcpyHostToDevice, h->stream));
+    LFX_CUDA(h, cudaMemcpyAsync(h->d_conv_tile_cloud.p, tile_cloud.data(), sizeof(uint32_t) * tiles, cudaMemcpyHostToDevice, h->stream));
     LFX_CUDA(h, cudaMemsetAsync(h->d_conv_state.p, 0, sizeof(unsigned long long) * tiles, h->stream));
     LFX_CUDA(h, cudaMemsetAsync(h->d_conv_meta.p, 0, sizeof(uint32_t) * (1 + 2 * (size_t)n_clouds), h->stream));
     ConvArgs a;
     a.clouds = h->d_conv_clouds.p;
     a.n_clouds = n_clouds;
     a.n_tiles = tiles;
+    a.tile_cloud = h->d_conv_tile_cloud.p;
     a.tile_state = h->d_conv_state.p;
     a.ticket = h->d_conv_meta.p;
     a.kept = h->d_conv_meta.p + 1;
     a.flags = h->d_conv_meta.p + 1 + n_clouds;
-    k_convert<<<tiles, CONV_TILE, (size_t)CONV_TILE * max_step, h->stream>>>(a);
+    if (!h->conv_smem_set) {
+      LFX_CUDA(h, cudaFuncSetAttribute(k_convert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_STAGE_MAX_BYTES));
+      LFX_CUDA(h, cudaFuncSetAttribute(k_convert<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_STAGE_MAX_BYTES));
+      for (auto & ev : h->conv_ev) { LFX_CUDA(h, cudaEventCreate(&ev)); }
+      h->conv_smem_set = true;
+    }
+    LFX_CUDA(h, cudaEventRecord(h->conv_ev[0], h->stream));
+    a.buf_bytes = ((uint32_t)CONV_TILE * max_step + 127u) & ~127u;
+    if (all_fast) { k_convert<true><<<tiles, CONV_THREADS, (size_t)a.buf_bytes, h->stream>>>(a); }
+    else { k_convert<false><<<tiles, CONV_THREADS, (size_t)a.buf_bytes, h->stream>>>(a); }
     LFX_CUDA(h, cudaGetLastError());
+    LFX_CUDA(h, cudaEventRecord(h->conv_ev[1], h->stream));
     h->launches += 1;
     std::vector<uint32_t> meta((size_t)2 * n_clouds);
     LFX_CUDA(h, cudaMemcpyAsync(meta.data(), h->d_conv_meta.p + 1, sizeof(uint32_t) * 2 * (size_t)n_clouds, cudaMemcpyDeviceToHost, h->stream));
@@ -1215,6 +1241,16 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
     out->status = h->conv_status.data();
   }
   return rc_all;
+}
+
+int lfx_last_convert_ms(lfx_handle * h, float * ms)
+{
+  if (!h || !ms) { return LFX_E_BAD_PARAM; }
+  if (!h->have_conv || !h->conv_ev[0]) { return fail(h, LFX_E_STATE, "no batch has been converted"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaEventSynchronize(h->conv_ev[1]));
+  LFX_CUDA(h, cudaEventElapsedTime(ms, h->conv_ev[0], h->conv_ev[1]));
+  return LFX_OK;
 }
 
 int lfx_converted_view(lfx_handle * h, int cloud, lfx_cloud_view * out)

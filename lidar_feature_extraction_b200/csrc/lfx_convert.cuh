@@ -7,9 +7,10 @@
 //
 // The struct-format quirks of the reference (effective offsets, positional packing, which fields are tested
 // for zero) are resolved on the host into a ConvCloud read plan (lfx_api.cu: conv_make_plan); what runs here
-// is byte work: one pass over the input, one CTA per tile of 256 points, the tile staged in shared memory
-// with 16-byte loads, a stable stream compaction (ballot ranks inside the tile, decoupled look-back over the
-// tiles of the same cloud) and two 16-byte stores per kept point. Bound: HBM, point_step + 32 * kept bytes
+// is byte work: one pass over the input, one CTA per tile of 512 points, the tile staged in shared memory by
+// one 1-D bulk copy of the TMA unit (cp.async.bulk + mbarrier), a stable stream compaction (ballot ranks inside
+// the tile, decoupled look-back over the tiles of the same cloud, output values decoded while the look-back
+// runs) and two 16-byte stores per kept point. Bound: HBM, point_step + 32 * kept bytes
 // per point.
 #ifndef LFX_CONVERT_CUH_
 #define LFX_CONVERT_CUH_
@@ -20,8 +21,13 @@
 namespace lfxk
 {
 
-constexpr int CONV_TILE = 256;          // points per CTA = threads per CTA
-constexpr int CONV_STAGE_MAX_STEP = 160; // larger points are decoded straight from global memory
+constexpr int CONV_THREADS = 256;
+#ifndef LFX_CONV_PPT
+#define LFX_CONV_PPT 2
+#endif
+constexpr int CONV_PPT = LFX_CONV_PPT;              // points per thread
+constexpr int CONV_TILE = CONV_PPT * CONV_THREADS;  // points per CTA
+constexpr int CONV_STAGE_MAX_BYTES = 48 * 1024;     // a tile of larger points is decoded straight from global memory
 constexpr int CONV_N_SLOTS = 9;         // [0..2] zero-test fields, [3..8] the six output slots
 
 // per-cloud flags raised by the kernel (struct.pack's data-dependent failures, convert.py:104-107)
@@ -40,7 +46,8 @@ struct ConvCloud
   uint8_t big;            // is_bigendian
   uint8_t packable;       // exactly six retained fields and an integer ring: points are written
   uint8_t staged;         // tile goes through shared memory
-  uint8_t pad[2];
+  uint8_t fast;           // little-endian, every slot naturally aligned, float32 everywhere but an unsigned ring
+  uint8_t pad[1];
 };
 
 struct ConvArgs
@@ -48,6 +55,8 @@ struct ConvArgs
   const ConvCloud * clouds;
   int n_clouds;
   uint32_t n_tiles;
+  uint32_t buf_bytes;               // size of one staging buffer (multiple of 128)
+  const uint32_t * tile_cloud;      // [n_tiles] owner of each tile
   unsigned long long * tile_state;  // [n_tiles] status << 62 | count
   uint32_t * ticket;
   uint32_t * kept;                  // [n_clouds]
@@ -132,107 +141,192 @@ __device__ __forceinline__ uint32_t conv_to_u16(unsigned long long raw, uint32_t
 
 constexpr unsigned long long CONV_ST_PARTIAL = 1ull << 62, CONV_ST_INCLUSIVE = 2ull << 62, CONV_ST_VALUE = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(CONV_TILE)
+// ---- 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier
+__device__ __forceinline__ void conv_mbar_init(uint64_t * bar)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void conv_bulk_load(void * smem_dst, const void * gsrc, uint32_t bytes, uint64_t * bar)
+{
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void conv_mbar_wait(uint64_t * bar, uint32_t parity)
+{
+  const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(b), "r"(parity) : "memory");
+  }
+}
+
+// One CTA per tile (CONV_TILE = CONV_PPT * CONV_THREADS consecutive points of one cloud), tiles handed out in
+// ticket order so that the look-back never waits on a tile that has not started. Thread t owns points t,
+// t + 256, ... of the tile: a warp's ballot covers 32 consecutive points and ranks stay stable. (A persistent
+// variant with two staging buffers measured 4x slower on B200: with all resident CTAs in lock step every
+// look-back has to walk the whole window of concurrently processed tiles.)
+// FAST: every cloud of the batch has the common plan (ConvCloud::fast): fields are single 32-bit loads and the
+// datatype dispatch disappears; the generic instantiation decodes any plan byte by byte.
+template<bool FAST>
+__global__ void __launch_bounds__(CONV_THREADS)
 k_convert(const ConvArgs a)
 {
-  extern __shared__ __align__(16) uint8_t conv_raw[];
-  __shared__ uint32_t s_tile, s_cloud, s_warp[CONV_TILE / 32];
+  extern __shared__ __align__(128) uint8_t conv_raw[];
+  __shared__ uint32_t s_tile[1], s_cnt[CONV_PPT * CONV_THREADS / 32];
   __shared__ unsigned long long s_excl;
-  __shared__ ConvCloud s_cc;
+  __shared__ __align__(8) uint64_t s_bar[1];
+  __shared__ ConvCloud s_cc[1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); }   // tiles start in order: look-back never waits on a tile that has not started
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  if (tile >= a.n_tiles) { return; }
-  if (tid == 0) {
-    int lo = 0, hi = a.n_clouds - 1;   // last cloud whose first tile is <= tile (clouds without points own no tile)
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (a.clouds[mid].tile_base <= tile) { lo = mid; } else { hi = mid - 1; }
-    }
-    s_cloud = (uint32_t)lo;
-  }
-  __syncthreads();
-  const int c = (int)s_cloud;
-  if (tid < (int)(sizeof(ConvCloud) / 4)) { reinterpret_cast<uint32_t *>(&s_cc)[tid] = reinterpret_cast<const uint32_t *>(a.clouds + c)[tid]; }
-  __syncthreads();
-  const ConvCloud & cc = s_cc;
-  const uint32_t t_in = tile - cc.tile_base;
-  const uint32_t p0 = t_in * CONV_TILE;
-  const int np = (int)min((uint32_t)CONV_TILE, cc.n_points - p0);
-  const uint32_t step = cc.point_step;
-  const uint8_t * src = cc.data + (size_t)p0 * step;
-  const uint8_t * mine = src + (size_t)tid * step;
-  if (cc.staged) {
-    const uint32_t bytes = (uint32_t)np * step, vec = bytes & ~15u;   // src is 16-byte aligned: data is, and 256 * step
-    for (uint32_t i = (uint32_t)tid * 16u; i < vec; i += CONV_TILE * 16u) {
-      *reinterpret_cast<uint4 *>(conv_raw + i) = __ldcs(reinterpret_cast<const uint4 *>(src + i));
-    }
-    for (uint32_t i = vec + (uint32_t)tid; i < bytes; i += CONV_TILE) { conv_raw[i] = src[i]; }
+  if (tid == 0) { conv_mbar_init(&s_bar[0]); }
+  uint32_t phase[1] = {0u};
+
+  // take a ticket and start staging that tile into buffer b
+  auto fetch = [&](int b) {
+    if (tid == 0) { s_tile[b] = atomicAdd(a.ticket, 1u); }
     __syncthreads();
-    mine = conv_raw + (size_t)tid * step;
-  }
-  const bool big = cc.big != 0;
-  bool keep = false;
-  if (tid < np) {
-    bool zero = true;
-#pragma unroll
-    for (int f = 0; f < 3; f++) { zero = zero && conv_is_zero(conv_load(mine + cc.off[f], cc.dt[f], cc.aligned[f] != 0, big), cc.dt[f]); }
-    keep = !zero;
-  }
-  // stable ranks inside the tile
-  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-  if (lane == 0) { s_warp[warp] = __popc(bal); }
+    const uint32_t tile = s_tile[b];
+    if (tile >= a.n_tiles) { return; }
+    const int c = (int)a.tile_cloud[tile];
+    if (tid < (int)(sizeof(ConvCloud) / 4)) { reinterpret_cast<uint32_t *>(&s_cc[b])[tid] = reinterpret_cast<const uint32_t *>(a.clouds + c)[tid]; }
+    __syncthreads();
+    const ConvCloud & cc = s_cc[b];
+    if (!cc.staged) { return; }
+    const uint32_t p0 = (tile - cc.tile_base) * CONV_TILE;
+    const uint32_t np = min((uint32_t)CONV_TILE, cc.n_points - p0);
+    const uint8_t * src = cc.data + (size_t)p0 * cc.point_step;   // 16-byte aligned: the cloud's data pointer is, and CONV_TILE * step
+    uint8_t * dst = conv_raw + (size_t)b * a.buf_bytes;
+    const uint32_t bytes = np * cc.point_step, vec = bytes & ~15u;
+    if (tid == 0 && vec) { conv_bulk_load(dst, src, vec, &s_bar[b]); }
+    for (uint32_t i = vec + (uint32_t)tid; i < bytes; i += CONV_THREADS) { dst[i] = src[i]; }
+  };
+
   __syncthreads();
-  uint32_t before = 0, total = 0;
+  fetch(0);
+  {
+    constexpr int cur = 0;
+    const uint32_t tile = s_tile[cur];
+    if (tile >= a.n_tiles) { return; }
+    const ConvCloud & cc = s_cc[cur];
+    const int c = (int)a.tile_cloud[tile];
+    const uint32_t t_in = tile - cc.tile_base;
+    const uint32_t p0 = t_in * CONV_TILE;
+    const int np = (int)min((uint32_t)CONV_TILE, cc.n_points - p0);
+    const uint32_t step = cc.point_step;
+    const uint8_t * base = cc.data + (size_t)p0 * step;
+    if (cc.staged) {
+      if (((uint32_t)np * step) & ~15u) { conv_mbar_wait(&s_bar[cur], phase[cur]); phase[cur] ^= 1u; }
+      base = conv_raw + (size_t)cur * a.buf_bytes;
+    }
+    __syncthreads();   // the tail bytes written by fetch() are visible
+    const bool big = cc.big != 0;
+    uint32_t keep = 0, bal[CONV_PPT];
 #pragma unroll
-  for (int w = 0; w < CONV_TILE / 32; w++) { const uint32_t n = s_warp[w]; if (w < warp) { before += n; } total += n; }
-  const uint32_t rank = before + __popc(bal & ((1u << lane) - 1u));
-  // decoupled look-back over the earlier tiles of the same cloud
-  if (warp == 0) {
-    unsigned long long * st = a.tile_state + cc.tile_base;
-    unsigned long long excl = 0;
-    if (t_in == 0) {
-      if (lane == 0) { *reinterpret_cast<volatile unsigned long long *>(st) = CONV_ST_INCLUSIVE | total; }
-    } else {
-      if (lane == 0) { *reinterpret_cast<volatile unsigned long long *>(st + t_in) = CONV_ST_PARTIAL | total; }
-      long long p = (long long)t_in - 1;
-      for (;;) {
-        const long long q = p - lane;
-        unsigned long long v = CONV_ST_INCLUSIVE;   // before the cloud's first tile: prefix 0
-        if (q >= 0) {
-          do { v = *reinterpret_cast<volatile unsigned long long *>(st + q); } while ((v >> 62) == 0);
+    for (int i = 0; i < CONV_PPT; i++) {
+      const int p = i * CONV_THREADS + tid;
+      bool k = false;
+      if (p < np) {
+        const uint8_t * mine = base + (size_t)p * step;
+        bool zero = true;
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+          if constexpr (FAST) { zero = zero && (*reinterpret_cast<const uint32_t *>(mine + cc.off[f]) & 0x7FFFFFFFu) == 0; }
+          else { zero = zero && conv_is_zero(conv_load(mine + cc.off[f], cc.dt[f], cc.aligned[f] != 0, big), cc.dt[f]); }
         }
-        const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-        const int first = incl ? __ffs(incl) - 1 : 32;   // nearest tile that already knows its inclusive prefix
-        unsigned long long add = lane <= first ? (v & CONV_ST_VALUE) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { add += __shfl_xor_sync(0xFFFFFFFFu, add, o); }
-        excl += add;
-        if (incl) { break; }
-        p -= 32;
+        k = !zero;
       }
-      if (lane == 0) { *reinterpret_cast<volatile unsigned long long *>(st + t_in) = CONV_ST_INCLUSIVE | (excl + total); }
+      bal[i] = __ballot_sync(0xFFFFFFFFu, k);
+      keep |= (k ? 1u : 0u) << i;
+      if (lane == 0) { s_cnt[i * (CONV_THREADS / 32) + warp] = __popc(bal[i]); }
     }
-    if (lane == 0) {
-      s_excl = excl;
-      if (p0 + (uint32_t)np == cc.n_points) { a.kept[c] = (uint32_t)(excl + total); }
-    }
-  }
-  __syncthreads();
-  if (!keep || !cc.packable) { return; }
-  bool overflow = false, range = false;
-  uint32_t w[6];
+    __syncthreads();
+    // warp 0: stable ranks inside the tile + decoupled look-back over the earlier tiles of the same cloud;
+    // the other warps decode their output values meanwhile
+    uint32_t rank_base[CONV_PPT];
+    if (warp == 0) {
+      constexpr int NC = CONV_PPT * CONV_THREADS / 32;
+      static_assert(NC <= 32, "one lane per (pass, warp) count");
+      const uint32_t mine = lane < NC ? s_cnt[lane] : 0u;
+      uint32_t inc = mine;
 #pragma unroll
-  for (int s = 0; s < 5; s++) {
-    const int f = 3 + s;
-    w[s] = conv_to_f32(conv_load(mine + cc.off[f], cc.dt[f], cc.aligned[f] != 0, big), cc.dt[f], overflow);
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) { inc += v; } }
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+      __syncwarp();
+      if (lane < NC) { s_cnt[lane] = inc - mine; }
+      unsigned long long * st = a.tile_state + cc.tile_base;
+      unsigned long long excl = 0;
+      if (t_in == 0) {
+        if (lane == 0) { *reinterpret_cast<volatile unsigned long long *>(st) = CONV_ST_INCLUSIVE | total; }
+      } else {
+        if (lane == 0) { *reinterpret_cast<volatile unsigned long long *>(st + t_in) = CONV_ST_PARTIAL | total; }
+        long long p = (long long)t_in - 1;
+        for (;;) {
+          const long long q = p - lane;
+          unsigned long long v = CONV_ST_INCLUSIVE;   // before the cloud's first tile: prefix 0
+          if (q >= 0) {
+            do { v = *reinterpret_cast<volatile unsigned long long *>(st + q); } while ((v >> 62) == 0);
+          }
+          const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+          const int first = incl ? __ffs(incl) - 1 : 32;   // nearest tile that already knows its inclusive prefix
+          unsigned long long add = lane <= first ? (v & CONV_ST_VALUE) : 0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { add += __shfl_xor_sync(0xFFFFFFFFu, add, o); }
+          excl += add;
+          if (incl) { break; }
+          p -= 32;
+        }
+        if (lane == 0) { *reinterpret_cast<volatile unsigned long long *>(st + t_in) = CONV_ST_INCLUSIVE | (excl + total); }
+      }
+      if (lane == 0) {
+        s_excl = excl;
+        if (p0 + (uint32_t)np == cc.n_points) { a.kept[c] = (uint32_t)(excl + total); }
+      }
+    }
+    bool overflow = false, range = false;
+    uint32_t w[CONV_PPT][6];
+    if (cc.packable) {
+#pragma unroll
+      for (int i = 0; i < CONV_PPT; i++) {
+        if (!((keep >> i) & 1u)) { continue; }
+        const uint8_t * mine = base + (size_t)(i * CONV_THREADS + tid) * step;
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+          const int f = 3 + s;
+          if constexpr (FAST) {
+            const uint32_t b = *reinterpret_cast<const uint32_t *>(mine + cc.off[f]);
+            w[i][s] = (b & 0x7FFFFFFFu) > 0x7F800000u ? (b | 0x00400000u) : b;
+          } else {
+            w[i][s] = conv_to_f32(conv_load(mine + cc.off[f], cc.dt[f], cc.aligned[f] != 0, big), cc.dt[f], overflow);
+          }
+        }
+        if constexpr (FAST) {
+          const uint8_t * rp = mine + cc.off[8];
+          const uint32_t r = cc.dt[8] == 2 ? (uint32_t)*rp : (cc.dt[8] == 4 ? (uint32_t)*reinterpret_cast<const uint16_t *>(rp) : *reinterpret_cast<const uint32_t *>(rp));
+          if (r > 65535u) { range = true; }
+          w[i][5] = r & 0xFFFFu;
+        } else {
+          w[i][5] = conv_to_u16(conv_load(mine + cc.off[8], cc.dt[8], cc.aligned[8] != 0, big), cc.dt[8], range);
+        }
+      }
+    }
+    __syncthreads();   // s_excl and the rank bases are published; every thread is done with the staging buffer
+    if (cc.packable && keep) {
+      const unsigned long long excl = s_excl;
+#pragma unroll
+      for (int i = 0; i < CONV_PPT; i++) {
+        if (!((keep >> i) & 1u)) { continue; }
+        rank_base[i] = s_cnt[i * (CONV_THREADS / 32) + warp];
+        const uint32_t rank = rank_base[i] + __popc(bal[i] & ((1u << lane) - 1u));
+        uint4 * dst = reinterpret_cast<uint4 *>(cc.out + (size_t)(excl + rank) * 32);
+        __stcs(dst, make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]));
+        __stcs(dst + 1, make_uint4(w[i][4], w[i][5], 0u, 0u));
+      }
+      if (overflow || range) { atomicOr(&a.flags[c], (overflow ? CONV_F_OVERFLOW : 0u) | (range ? CONV_F_RING_RANGE : 0u)); }
+    }
   }
-  w[5] = conv_to_u16(conv_load(mine + cc.off[8], cc.dt[8], cc.aligned[8] != 0, big), cc.dt[8], range);
-  uint4 * dst = reinterpret_cast<uint4 *>(cc.out + (size_t)(s_excl + rank) * 32);
-  __stcs(dst, make_uint4(w[0], w[1], w[2], w[3]));
-  __stcs(dst + 1, make_uint4(w[4], w[5], 0u, 0u));
-  if (overflow || range) { atomicOr(&a.flags[c], (overflow ? CONV_F_OVERFLOW : 0u) | (range ? CONV_F_RING_RANGE : 0u)); }
 }
 
 }  // namespace lfxk

@@ -202,3 +202,34 @@ def test_device_resident_input_and_chaining_into_the_extraction():
         out = fe.fetch()
         compare_scan(out, 0, want_cloud, want)
         compare_scan(out, 1, want_cloud, want)
+
+
+def test_common_plan_fast_kernel_special_values(conv):
+    """The all-float32 little-endian plan runs on the specialised instantiation: signalling NaNs come out quiet
+    with their payload, -0.0 counts as zero, a uint32 ring above 65535 fails like struct.pack('H')."""
+    from lidar_feature_extraction_b200 import ConvertError
+    from oracle import convert_oracle as co
+
+    rng = np.random.default_rng(11)
+    n = 3000
+    fields = [co.Field("x", 0, 7), co.Field("y", 4, 7), co.Field("z", 8, 7), co.Field("intensity", 16, 7), co.Field("ring", 20, 6)]
+    raw = np.zeros((n, 24), np.uint8)
+    f = rng.normal(0, 10, (n, 4)).astype("<f4")
+    bits = f.view(np.uint32)
+    bits[rng.random((n, 4)) < 0.05] = 0x7F800001 + rng.integers(0, 0x3FFFFF)       # signalling NaNs with payloads
+    bits[rng.random((n, 4)) < 0.05] = 0xFFC12345
+    bits[rng.random((n, 4)) < 0.02] = 0x7F800000                                     # inf
+    bits[rng.random((n, 4)) < 0.02] = 0x00000001                                     # denormal
+    zero = rng.random(n) < 0.2
+    bits[zero, :3] = rng.choice(np.array([0, 0x80000000], np.uint32), (int(zero.sum()), 3))   # +-0.0
+    raw[:, 0:12] = f[:, :3].view(np.uint8).reshape(n, 12)
+    raw[:, 16:20] = f[:, 3:].view(np.uint8).reshape(n, 4)
+    raw[:, 20:24] = rng.integers(0, 65536, n).astype("<u4").view(np.uint8).reshape(n, 4)
+    want = _oracle(raw, fields, 24, False)
+    assert want is not None and 0 < want.shape[0] < n
+    assert np.array_equal(conv.callback(_msg(raw, fields, 24, False)).data, want)
+    raw[n // 2, 20:24] = np.array([65536], "<u4").view(np.uint8)
+    raw[n // 2, 0:4] = np.array([1.0], "<f4").view(np.uint8)
+    assert _oracle(raw, fields, 24, False) is None
+    with pytest.raises(ConvertError):
+        conv.callback(_msg(raw, fields, 24, False))
