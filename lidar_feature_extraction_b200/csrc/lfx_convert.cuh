@@ -164,8 +164,7 @@ __device__ __forceinline__ void conv_mbar_wait(uint64_t * bar, uint32_t parity)
   }
 }
 
-// One CTA per tile (CONV_TILE = CONV_PPT * CONV_THREADS consecutive points of one cloud), tiles handed out in
-// ticket order so that the look-back never waits on a tile that has not started. Thread t owns points t,
+// One CTA per tile (CONV_TILE = CONV_PPT * CONV_THREADS consecutive points of one cloud). Thread t owns points t,
 // t + 256, ... of the tile: a warp's ballot covers 32 consecutive points and ranks stay stable. (A persistent
 // variant with two staging buffers measured 4x slower on B200: with all resident CTAs in lock step every
 // look-back has to walk the whole window of concurrently processed tiles.)
@@ -184,12 +183,11 @@ k_convert(const ConvArgs a)
   if (tid == 0) { conv_mbar_init(&s_bar[0]); }
   uint32_t phase[1] = {0u};
 
-  // take a ticket and start staging that tile into buffer b
+  // start staging this CTA's tile into buffer b. Tile = blockIdx.x: CTAs of a 1-D grid are dispatched in index
+  // order, so every earlier tile has started (the same assumption CUB's decoupled look-back scan makes).
   auto fetch = [&](int b) {
-    if (tid == 0) { s_tile[b] = atomicAdd(a.ticket, 1u); }
-    __syncthreads();
-    const uint32_t tile = s_tile[b];
-    if (tile >= a.n_tiles) { return; }
+    const uint32_t tile = blockIdx.x;
+    if (tid == 0) { s_tile[b] = tile; }
     const int c = (int)a.tile_cloud[tile];
     if (tid < (int)(sizeof(ConvCloud) / 4)) { reinterpret_cast<uint32_t *>(&s_cc[b])[tid] = reinterpret_cast<const uint32_t *>(a.clouds + c)[tid]; }
     __syncthreads();
@@ -204,7 +202,6 @@ k_convert(const ConvArgs a)
     for (uint32_t i = vec + (uint32_t)tid; i < bytes; i += CONV_THREADS) { dst[i] = src[i]; }
   };
 
-  __syncthreads();
   fetch(0);
   {
     constexpr int cur = 0;
