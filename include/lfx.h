@@ -262,6 +262,30 @@ int lfx_converted_view(lfx_handle *h, int cloud, lfx_cloud_view *out);
 /* Copies converted cloud `cloud` (32 * kept bytes = PointCloud2.data of /points_converted) to host memory. */
 int lfx_fetch_converted(lfx_handle *h, int cloud, void *dst, size_t capacity_bytes);
 
+/* ------------------------------------------------------------------ colored_scan + message layouts
+ * Replaces ColorPointsByLabel (extraction/include/lidar_feature_extraction/color_points.hpp:60-74) as the node
+ * uses it (feature_extraction.cpp:153,161,168): all points of the rings that contribute to the outputs (not
+ * sparse, not skipped), rings ascending, ring-sorted order, as 32-byte pcl::PointXYZRGB records
+ * x,y,z,1.0f,{b,g,r,a=255},12 zero bytes. Needs lfx_options.want_sorted_src. Synchronous. Arrays of the result
+ * are host memory owned by the handle; d_points is device memory: scan s owns counts[s] points at
+ * d_points + 32 * point_base[s]. Valid until the next lfx_extract_batch / lfx_color_batch. */
+typedef struct lfx_colored_result {
+  int n_scans;
+  const uint8_t *d_points;
+  const uint64_t *point_base;   /* [n_scans + 1] */
+  const uint32_t *counts;       /* [n_scans] */
+} lfx_colored_result;
+int lfx_color_batch(lfx_handle *h, lfx_colored_result *out);
+int lfx_fetch_colored(lfx_handle *h, int scan, void *dst, size_t capacity_bytes);
+
+/* PointCloud2 layout of the node's three output topics, i.e. what pcl::toROSMsg makes of pcl::PointXYZ
+ * (scan_edge, scan_surface: x,y,z FLOAT32 @0,4,8, point_step 16) and pcl::PointXYZRGB (colored_scan: x,y,z
+ * @0,4,8 and rgb FLOAT32 @16, point_step 32) - lib/include/lidar_feature_library/ros_msg.hpp:53-71. The
+ * library's feature / colored buffers are exactly PointCloud2.data of these messages (height 1, width n,
+ * little-endian, is_dense, frame "lidar_feature_base_link", stamp of the input: feature_extraction.cpp:159-166). */
+enum { LFX_TOPIC_SCAN_EDGE = 0, LFX_TOPIC_SCAN_SURFACE = 1, LFX_TOPIC_COLORED_SCAN = 2 };
+int lfx_topic_layout(int topic, lfx_point_field *fields /* capacity 4 */, uint32_t *n_fields, uint32_t *point_step);
+
 /* ------------------------------------------------------------------ memory helpers */
 /* Pinned host memory so that H2D/D2H run at full PCIe speed. */
 void *lfx_host_alloc(size_t bytes);

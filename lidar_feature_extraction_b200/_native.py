@@ -26,6 +26,7 @@ LFX_MEM_HOST, LFX_MEM_DEVICE = 0, 1
 LFX_RING_U8, LFX_RING_U16, LFX_RING_U32 = 2, 4, 6
 LFX_RING_OK, LFX_RING_SPARSE, LFX_RING_SKIPPED, LFX_RING_TOO_LONG = range(4)
 LFX_WORLD_ROOM, LFX_WORLD_TUNNEL = 0, 1
+LFX_TOPIC_SCAN_EDGE, LFX_TOPIC_SCAN_SURFACE, LFX_TOPIC_COLORED_SCAN = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -135,6 +136,11 @@ class ConvertResult(C.Structure):
                 ("kept", C.POINTER(C.c_uint32)), ("status", C.POINTER(C.c_uint32))]
 
 
+class ColoredResult(C.Structure):
+    _fields_ = [("n_scans", C.c_int), ("d_points", C.c_void_p), ("point_base", C.POINTER(C.c_uint64)),
+                ("counts", C.POINTER(C.c_uint32))]
+
+
 class SynthSpec(C.Structure):
     _fields_ = [
         ("n_rings", C.c_int),
@@ -216,6 +222,9 @@ def lib() -> C.CDLL:
     L.lfx_last_convert_ms.argtypes = [H, C.POINTER(C.c_float)]
     L.lfx_converted_view.argtypes = [H, C.c_int, C.POINTER(CloudView)]
     L.lfx_fetch_converted.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
+    L.lfx_color_batch.argtypes = [H, C.POINTER(ColoredResult)]
+    L.lfx_fetch_colored.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
+    L.lfx_topic_layout.argtypes = [C.c_int, C.POINTER(PointFieldC), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]
     L.lfx_synth_scan_host.argtypes = [C.POINTER(SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
     L.lfx_synth_batch_device.argtypes = [H, C.POINTER(SynthSpec), C.c_uint64, C.c_int, C.c_void_p]

@@ -23,6 +23,7 @@
 #include "lfx_sector.cuh"
 #include "lfx_synth.h"
 #include "lfx_convert.cuh"
+#include "lfx_color.cuh"
 
 using namespace lfxk;
 
@@ -105,6 +106,12 @@ struct lfx_handle
   std::vector<uint64_t> conv_point_base;
   std::vector<uint32_t> conv_kept, conv_status;
   bool have_conv = false;
+  // colored_scan (lfx_color_batch)
+  DevBuf<uint4> d_colored;
+  DevBuf<uint32_t> d_colored_counts;
+  std::vector<uint32_t> colored_counts;
+  std::vector<uint64_t> colored_base;
+  bool have_colored = false;
 
   // pinned host staging
   ScanDesc * h_scans = nullptr;
@@ -566,6 +573,7 @@ void lfx_destroy(lfx_handle * h)
   for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_bndx[c].p); }
   cudaFree(h->d_ring_path.p);
   cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p); cudaFree(h->d_conv_tile_cloud.p);
+  cudaFree(h->d_colored.p); cudaFree(h->d_colored_counts.p);
   for (auto & ev : h->conv_ev) { if (ev) { cudaEventDestroy(ev); } }
   cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
@@ -586,6 +594,7 @@ int lfx_device(const lfx_handle * h) { return h ? h->device : -1; }
 int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans, lfx_batch_result * out)
 {
   if (!h) { return LFX_E_BAD_PARAM; }
+  h->have_colored = false;
   if (n_scans < 0 || (n_scans > 0 && !scans)) { return fail(h, LFX_E_BAD_PARAM, "bad scans argument"); }
   LFX_CUDA(h, cudaSetDevice(h->device));
   h->have_batch = false;
@@ -1283,6 +1292,84 @@ int lfx_fetch_converted(lfx_handle * h, int cloud, void * dst, size_t capacity_b
   LFX_CUDA(h, cudaSetDevice(h->device));
   LFX_CUDA(h, cudaMemcpyAsync(dst, h->d_conv_out.p + h->conv_point_base[(size_t)cloud] * 32, bytes, cudaMemcpyDeviceToHost, h->stream));
   LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- colored_scan + message layouts
+
+extern "C" {
+
+int lfx_color_batch(lfx_handle * h, lfx_colored_result * out)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  if (!h->opt.want_sorted_src) { return fail(h, LFX_E_STATE, "colored_scan needs lfx_options.want_sorted_src"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  const int ns = h->n_scans;
+  h->have_colored = false;
+  h->colored_counts.assign((size_t)ns, 0);
+  h->colored_base.assign(h->h_point_base, h->h_point_base + ns + 1);
+  if (ns > 0) {
+    int rc;
+    if ((rc = ensure(h, h->d_colored, (size_t)h->total_points * 2 + 2, nullptr))) { return rc; }
+    if ((rc = ensure(h, h->d_colored_counts, (size_t)ns, nullptr))) { return rc; }
+    ColorArgs a;
+    a.scans = h->d_scans.p;
+    a.rings = h->d_rings.p;
+    a.labels = h->d_labels.p;
+    a.sorted_src = h->d_sorted_src.p;
+    a.out = h->d_colored.p;
+    a.counts = h->d_colored_counts.p;
+    a.max_rings = h->opt.max_rings;
+    for (int s0 = 0; s0 < ns; s0 += 65535) {   // grid.y limit
+      ColorArgs b = a;
+      b.scans += s0; b.rings += (size_t)s0 * a.max_rings; b.counts += s0;
+      k_color_scan<<<dim3((unsigned)a.max_rings, (unsigned)std::min(ns - s0, 65535)), COLOR_THREADS, 0, h->stream>>>(b);
+      LFX_CUDA(h, cudaGetLastError());
+      h->launches += 1;
+    }
+    LFX_CUDA(h, cudaMemcpyAsync(h->colored_counts.data(), h->d_colored_counts.p, sizeof(uint32_t) * (size_t)ns, cudaMemcpyDeviceToHost, h->stream));
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->have_colored = true;
+  if (out) {
+    out->n_scans = ns;
+    out->d_points = reinterpret_cast<const uint8_t *>(h->d_colored.p);
+    out->point_base = h->colored_base.data();
+    out->counts = h->colored_counts.data();
+  }
+  return LFX_OK;
+}
+
+int lfx_fetch_colored(lfx_handle * h, int scan, void * dst, size_t capacity_bytes)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_colored) { return fail(h, LFX_E_STATE, "lfx_color_batch has not run for this batch"); }
+  if (scan < 0 || (size_t)scan >= h->colored_counts.size()) { return fail(h, LFX_E_BAD_PARAM, "scan index out of range"); }
+  const size_t bytes = (size_t)h->colored_counts[(size_t)scan] * 32;
+  if (bytes > capacity_bytes || (bytes > 0 && !dst)) { return fail(h, LFX_E_BAD_PARAM, "destination too small"); }
+  if (bytes == 0) { return LFX_OK; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMemcpyAsync(dst, reinterpret_cast<const uint8_t *>(h->d_colored.p) + h->colored_base[(size_t)scan] * 32, bytes, cudaMemcpyDeviceToHost, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_topic_layout(int topic, lfx_point_field * fields, uint32_t * n_fields, uint32_t * point_step)
+{
+  if (!fields || !n_fields || !point_step) { return LFX_E_BAD_PARAM; }
+  if (topic != LFX_TOPIC_SCAN_EDGE && topic != LFX_TOPIC_SCAN_SURFACE && topic != LFX_TOPIC_COLORED_SCAN) { return LFX_E_BAD_PARAM; }
+  static const char * const names[4] = {"x", "y", "z", "rgb"};
+  for (int k = 0; k < 3; k++) { fields[k].name = names[k]; fields[k].offset = 4u * (uint32_t)k; fields[k].datatype = 7; fields[k].count = 1; }
+  *n_fields = 3;
+  *point_step = 16;   // sizeof(pcl::PointXYZ)
+  if (topic == LFX_TOPIC_COLORED_SCAN) {
+    fields[3].name = names[3]; fields[3].offset = 16; fields[3].datatype = 7; fields[3].count = 1;
+    *n_fields = 4;
+    *point_step = 32; // sizeof(pcl::PointXYZRGB)
+  }
   return LFX_OK;
 }
 

@@ -109,6 +109,16 @@ def label_to_color(label: int) -> tuple:
     return tuple(rgb)
 
 
+def topic_fields(topic: int) -> tuple:
+    """(fields, point_step) of one of the node's output topics (lfx_topic_layout; ros_msg.hpp:53-71)."""
+    arr = (N.PointFieldC * 4)()
+    n, step = C.c_uint32(), C.c_uint32()
+    rc = N.lib().lfx_topic_layout(topic, arr, C.byref(n), C.byref(step))
+    if rc != N.LFX_OK:
+        raise ValueError(f"unknown topic {topic}")
+    return [PointField(arr[k].name.decode(), arr[k].offset, arr[k].datatype, arr[k].count) for k in range(n.value)], step.value
+
+
 def _is_cuda_tensor(obj) -> bool:
     return hasattr(obj, "is_cuda") and bool(obj.is_cuda)
 
@@ -286,6 +296,18 @@ class FeatureExtraction:
             self._check(self._lib.lfx_memcpy_d2h(self._h, pb.ctypes.data, res.d_point_base, pb.nbytes))
         return BatchOutput(counts, offsets, edge, surf, labels, sorted_src, curv, rings, pb)
 
+    # -- colored_scan (feature_extraction.cpp:153,161,168)
+    def colored_scans(self) -> list:
+        """[n_i, 32] uint8 PointXYZRGB records of every scan of the last batch (needs want_sorted_src)."""
+        res = N.ColoredResult()
+        self._check(self._lib.lfx_color_batch(self._h, C.byref(res)))
+        out = []
+        for s in range(res.n_scans):
+            a = np.zeros((int(res.counts[s]), 32), np.uint8)
+            self._check(self._lib.lfx_fetch_colored(self._h, s, a.ctypes.data, a.nbytes))
+            out.append(a)
+        return out
+
     # -- the ROS-callback-shaped entry (feature_extraction.cpp:92-171)
     def callback(self, msg: PointCloud2) -> dict:
         """One PointCloud2 in; returns {"scan_edge", "scan_surface", "colored_scan"} PointCloud2 messages
@@ -300,15 +322,22 @@ class FeatureExtraction:
         out = N.ScanOutput()
         self._check(self._lib.lfx_extract_scan(self._h, C.byref(view), C.byref(out)))
 
-        def xyz_msg(ptr, n):
+        def xyz_msg(ptr, n, topic):
             pts = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(max(n, 1), 4))[:n].copy()
-            return PointCloud2(data=pts.view(np.uint8).reshape(n, 16), point_step=16, width=n, height=1,
-                               stamp=msg.stamp, frame_id=FRAME_ID,
-                               fields=[PointField("x", 0, FLOAT32), PointField("y", 4, FLOAT32), PointField("z", 8, FLOAT32)])
+            fields, step = topic_fields(topic)
+            return PointCloud2(data=pts.view(np.uint8).reshape(n, step), point_step=step, width=n, height=1,
+                               stamp=msg.stamp, frame_id=FRAME_ID, fields=fields)
 
         labels = np.ctypeslib.as_array(C.cast(out.labels, C.POINTER(C.c_uint8)), shape=(max(out.n_points, 1),))[: out.n_points].copy()
-        return {"scan_edge": xyz_msg(out.edge_xyz, out.n_edge), "scan_surface": xyz_msg(out.surface_xyz, out.n_surface),
-                "labels": labels, "stamp": msg.stamp, "frame_id": FRAME_ID}
+        res = {"scan_edge": xyz_msg(out.edge_xyz, out.n_edge, N.LFX_TOPIC_SCAN_EDGE),
+               "scan_surface": xyz_msg(out.surface_xyz, out.n_surface, N.LFX_TOPIC_SCAN_SURFACE),
+               "labels": labels, "stamp": msg.stamp, "frame_id": FRAME_ID}
+        if self.want_sorted_src:   # colored_scan is a debug topic: only built when the index map is kept
+            colored = self.colored_scans()[0]
+            fields, step = topic_fields(N.LFX_TOPIC_COLORED_SCAN)
+            res["colored_scan"] = PointCloud2(data=colored, point_step=step, width=colored.shape[0], height=1, stamp=msg.stamp,
+                                              frame_id=FRAME_ID, fields=fields)
+        return res
 
     def batch_stats(self) -> dict:
         """Which path the last batch took: rings on the sector kernel per lane class, scans/rings on the general path."""
