@@ -3,6 +3,8 @@
 // Mirrors, for the one path this library replaces:
 //   lfx::HyperParameters   extraction/include/lidar_feature_extraction/hyper_parameter.hpp:32-65
 //   lfx::FeatureExtraction the per-scan work of FeatureExtraction::Callback, extraction/app/feature_extraction.cpp:92-171
+//   lfx::PointTypeConverter the upstream converter node, point_type_converter/point_type_converter/convert.py:171-212
+//   lfx::TopicLayout / FeatureExtraction::ColoredScan  ToRosMsg<T> (ros_msg.hpp:53-71), ColorPointsByLabel (color_points.hpp:60-74)
 // No CUDA or ROS headers are needed to include this file; link with -llfx.
 #ifndef LFX_HPP_
 #define LFX_HPP_
@@ -92,9 +94,75 @@ public:
   void Synchronize() { Check(lfx_synchronize(h_)); }
   lfx_handle * handle() { return h_; }
 
+  // colored_scan of scan `scan` of the last batch (feature_extraction.cpp:153,161): 32-byte pcl::PointXYZRGB records,
+  // i.e. PointCloud2.data of the message; needs lfx_options.want_sorted_src (use the two-argument constructor).
+  FeatureExtraction(const HyperParameters & params, const lfx_options & opt)
+  {
+    const int rc = lfx_create(&params, &opt, &h_);
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(nullptr)); }
+  }
+  std::vector<uint8_t> ColoredScan(int scan = 0)
+  {
+    lfx_colored_result res;
+    Check(lfx_color_batch(h_, &res));
+    if (scan < 0 || scan >= res.n_scans) { throw Error(LFX_E_BAD_PARAM, "scan index out of range"); }
+    std::vector<uint8_t> data(static_cast<size_t>(res.counts[scan]) * 32);
+    Check(lfx_fetch_colored(h_, scan, data.data(), data.size()));
+    return data;
+  }
+
 private:
   void Check(int rc) { if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); } }
   lfx_handle * h_ = nullptr;
+};
+
+// fields + point_step of scan_edge / scan_surface / colored_scan (what pcl::toROSMsg derives, ros_msg.hpp:53-71)
+struct TopicLayout
+{
+  std::vector<PointField> fields;
+  uint32_t point_step = 0;
+  explicit TopicLayout(int topic)
+  {
+    lfx_point_field f[4];
+    uint32_t n = 0;
+    if (lfx_topic_layout(topic, f, &n, &point_step) != LFX_OK) { throw Error(LFX_E_BAD_PARAM, "unknown topic"); }
+    for (uint32_t k = 0; k < n; k++) { fields.push_back({f[k].name, f[k].offset, f[k].datatype}); }
+  }
+};
+
+// The upstream converter (convert.py:171-212) on the device. Shares the extraction handle so that converted clouds
+// feed ExtractBatch without leaving the GPU: Convert(raw clouds) -> View(i) -> FeatureExtraction::ExtractBatch.
+class PointTypeConverter
+{
+public:
+  explicit PointTypeConverter(FeatureExtraction & fe) : h_(fe.handle()) {}
+
+  // Returns the per-cloud outcome; clouds for which the reference's callback raises have status != LFX_CONVERT_OK.
+  lfx_convert_result Convert(const std::vector<lfx_raw_cloud> & clouds)
+  {
+    lfx_convert_result res;
+    const int rc = lfx_convert_batch(h_, clouds.data(), static_cast<int>(clouds.size()), &res);
+    if (rc != LFX_OK && rc != LFX_E_CONVERT) { throw Error(rc, lfx_last_error(h_)); }
+    return res;
+  }
+  lfx_cloud_view View(int cloud)
+  {
+    lfx_cloud_view v;
+    const int rc = lfx_converted_view(h_, cloud, &v);
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); }
+    return v;
+  }
+  // PointCloud2.data of /points_converted (convert.py:198-212: point_step 32, height 1, width = size / 32, is_dense)
+  std::vector<uint8_t> Fetch(int cloud, uint32_t kept)
+  {
+    std::vector<uint8_t> data(static_cast<size_t>(kept) * 32);
+    const int rc = lfx_fetch_converted(h_, cloud, data.data(), data.size());
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); }
+    return data;
+  }
+
+private:
+  lfx_handle * h_;
 };
 
 }  // namespace lfx

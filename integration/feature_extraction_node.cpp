@@ -27,6 +27,27 @@ static lfx::HyperParameters DeclareParameters(rclcpp::Node & node)
   return p;  // lfx_create re-checks positivity (hyper_parameter.hpp:45-53) and returns LFX_E_BAD_PARAM
 }
 
+// any of the three output topics from the library's byte buffer and lfx_topic_layout (ros_msg.hpp:53-71)
+static sensor_msgs::msg::PointCloud2 MakeCloud(int topic, const uint8_t * data, uint32_t n, const std_msgs::msg::Header & header)
+{
+  const lfx::TopicLayout layout(topic);
+  sensor_msgs::msg::PointCloud2 msg;
+  msg.header = header;
+  msg.height = 1;
+  msg.width = n;
+  msg.is_dense = true;
+  msg.is_bigendian = false;
+  msg.point_step = layout.point_step;
+  msg.row_step = layout.point_step * n;
+  for (const auto & lf : layout.fields) {
+    sensor_msgs::msg::PointField f;
+    f.name = lf.name; f.offset = lf.offset; f.datatype = lf.datatype; f.count = 1;
+    msg.fields.push_back(f);
+  }
+  msg.data.assign(data, data + static_cast<size_t>(layout.point_step) * n);
+  return msg;
+}
+
 static sensor_msgs::msg::PointCloud2 MakeXYZCloud(const float * xyzw, uint32_t n, const std_msgs::msg::Header & header)
 {
   // what pcl::toROSMsg emits for pcl::PointXYZ (ros_msg.hpp:53-71): x,y,z FLOAT32 at 0/4/8, point_step 16
@@ -52,7 +73,7 @@ class FeatureExtractionNode : public rclcpp::Node
 {
 public:
   FeatureExtractionNode()
-  : Node("lidar_feature_extraction"), fe_(DeclareParameters(*this), /*device=*/0)
+  : Node("lidar_feature_extraction"), fe_(DeclareParameters(*this), DebugOptions())
   {
     // feature_extraction.cpp:73-82 — same topics and QoS
     const auto qos = rclcpp::SensorDataQoS().reliable().durability_volatile();
@@ -60,9 +81,17 @@ public:
       "points_raw", qos, std::bind(&FeatureExtractionNode::Callback, this, std::placeholders::_1));
     edge_pub_ = create_publisher<sensor_msgs::msg::PointCloud2>("scan_edge", qos);
     surface_pub_ = create_publisher<sensor_msgs::msg::PointCloud2>("scan_surface", qos);
+    colored_pub_ = create_publisher<sensor_msgs::msg::PointCloud2>("colored_scan", 1);   // :77-78
   }
 
 private:
+  static lfx_options DebugOptions()
+  {
+    lfx_options opt{};
+    opt.want_sorted_src = 1;   // keeps the ring-sorted -> source index map that colored_scan needs
+    return opt;
+  }
+
   void Callback(const sensor_msgs::msg::PointCloud2::ConstSharedPtr msg)
   {
     std::vector<lfx::PointField> fields;
@@ -81,12 +110,17 @@ private:
     header.frame_id = "lidar_feature_base_link";      // feature_extraction.cpp:159
     edge_pub_->publish(MakeXYZCloud(out.edge_xyz, out.n_edge, header));           // :163-170
     surface_pub_->publish(MakeXYZCloud(out.surface_xyz, out.n_surface, header));
-    // colored_scan (depth-1 debug topic, :77-78): colour out.labels[i] with lfx_label_to_color on the host
+    // colored_scan (depth-1 debug topic, :77-78,153,161,168): built on the device when the handle was created with
+    // lfx_options.want_sorted_src; the bytes are PointCloud2.data of the pcl::PointXYZRGB message
+    if (colored_pub_->get_subscription_count() > 0) {
+      const std::vector<uint8_t> colored = fe_.ColoredScan();
+      colored_pub_->publish(MakeCloud(LFX_TOPIC_COLORED_SCAN, colored.data(), static_cast<uint32_t>(colored.size() / 32), header));
+    }
   }
 
   lfx::FeatureExtraction fe_;
   rclcpp::Subscription<sensor_msgs::msg::PointCloud2>::SharedPtr sub_;
-  rclcpp::Publisher<sensor_msgs::msg::PointCloud2>::SharedPtr edge_pub_, surface_pub_;
+  rclcpp::Publisher<sensor_msgs::msg::PointCloud2>::SharedPtr edge_pub_, surface_pub_, colored_pub_;
 };
 
 int main(int argc, char * argv[])
