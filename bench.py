@@ -299,17 +299,21 @@ def main():
     torch.cuda.synchronize()
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n_points = int(offs[-1])
-    dev_views = [FeatureExtraction.wire_view((d_in.data_ptr() + int(offs[s]) * 32, sizes[s])) for s in range(scans_per_gpu)]
+    dev_views = FeatureExtraction.view_array(
+        [FeatureExtraction.wire_view((d_in.data_ptr() + int(offs[s]) * 32, sizes[s])) for s in range(scans_per_gpu)])
+    # the path's only exchange: all-gather of per-scan (n_edge, n_surface) over NVLink on a side stream (it overlaps
+    # the next batch); global offsets follow from a local exclusive scan. join() puts it back on the timed stream.
+    gather_mode = os.environ.get("LFX_BENCH_GATHER", "sync")   # diagnosis only: sync (default) | overlap | none
+    sharded = sharding.ShardedExtraction(fe, n_frames, dev, overlap=(gather_mode == "overlap"))
+
     def step_device():
-        res = fe.extract_views(dev_views, keep=d_in)
-        if world > 1:
-            # the path's only exchange: all-gather of per-scan (n_edge, n_surface) over NVLink, enqueued on
-            # the extraction stream; global offsets follow from a local exclusive scan
-            sharding.gather_counts(sharding.device_counts_tensor(res, dev), n_frames)
-        return res
+        if gather_mode == "none":
+            return fe.extract_views(dev_views, keep=d_in)
+        return sharded.step(dev_views, keep=d_in)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    sharded.join()
     torch.cuda.synchronize()
     launches0 = fe.kernel_launches
     if world > 1:
@@ -325,6 +329,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
+    sharded.join()
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -385,6 +390,7 @@ def main():
         host_views = [FeatureExtraction.wire_view((hptr + int(offs[s]) * 32, sizes[s])) for s in range(scans_per_gpu)]
         for v in host_views:
             v.memory = N.LFX_MEM_HOST
+        host_views = FeatureExtraction.view_array(host_views)
         cap = n_points
         h_edge = lib.lfx_host_alloc(16 * max(n_feat, 1) * 2)
         h_surf = lib.lfx_host_alloc(16 * max(n_feat, 1) * 2)

@@ -237,11 +237,20 @@ class FeatureExtraction:
         return N.CloudView(data.ctypes.data, n, POINT_STEP, 0, 4, 8, 20, N.LFX_RING_U16, 1, 1, N.LFX_MEM_HOST)
 
     # -- batched entry
-    def extract_views(self, views: Sequence[N.CloudView], keep=None) -> N.BatchResult:
-        """Enqueue one batch (asynchronous). ``keep`` pins Python owners of the input buffers."""
+    @staticmethod
+    def view_array(views: Sequence[N.CloudView]):
+        """The C array lfx_extract_batch takes; build it once when the same views are extracted repeatedly
+        (marshalling a thousand structs costs more host time than the GPU needs for the batch)."""
         arr = (N.CloudView * max(len(views), 1))(*views)
+        arr.n_views = len(views)
+        return arr
+
+    def extract_views(self, views, keep=None) -> N.BatchResult:
+        """Enqueue one batch (asynchronous). ``views``: a sequence of CloudView or a ``view_array``.
+        ``keep`` pins Python owners of the input buffers."""
+        arr = views if hasattr(views, "n_views") else self.view_array(views)
         res = N.BatchResult()
-        self._check(self._lib.lfx_extract_batch(self._h, arr, len(views), C.byref(res)))
+        self._check(self._lib.lfx_extract_batch(self._h, arr, arr.n_views, C.byref(res)))
         self._last = res
         self._keep = keep
         return res

@@ -89,7 +89,9 @@ def _gpu_worker(rank, world, port, out_dir):
         fe = FeatureExtraction(HyperParameters(), device=rank, stream=stream.cuda_stream)
         drv = sharding.ShardedExtraction(fe, n_frames, dev)
         clouds = [torch.from_numpy(synth.scan_host(sp, f)).to(dev) for f in range(drv.lo, drv.hi)]
-        drv.step([fe.wire_view(c) for c in clouds], keep=clouds)
+        for _ in range(3):   # the gather runs on a side stream out of two rotating count buffers
+            drv.step([fe.wire_view(c) for c in clouds], keep=clouds)
+        drv.join()
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, f"gpu_counts_{rank}.npy"), drv.counts_all.cpu().numpy())
         fe.close()
