@@ -286,6 +286,27 @@ int lfx_fetch_colored(lfx_handle *h, int scan, void *dst, size_t capacity_bytes)
 enum { LFX_TOPIC_SCAN_EDGE = 0, LFX_TOPIC_SCAN_SURFACE = 1, LFX_TOPIC_COLORED_SCAN = 2 };
 int lfx_topic_layout(int topic, lfx_point_field *fields /* capacity 4 */, uint32_t *n_fields, uint32_t *point_step);
 
+/* ------------------------------------------------------------------ mapping accumulate
+ * Replaces, for the batched offline sequence, MapBuilder::Callback + Map::TransformAdd of the mapping package
+ * (mapping/include/lidar_feature_mapping/map.hpp:104-127, :68-74; thresholds :92-93): frame i of the last
+ * extracted batch is added to the map iff its scan_edge cloud is not empty and (the map is empty or the pose
+ * moved >= 1 m or rotated |dq.vec| >= 0.1 since the last ADDED frame: PoseDiffIsSufficientlySmall, :50-60); an
+ * added cloud is transformed by its pose (GetIsometry3d, lib/src/ros_msg.cpp:33-38; pcl::transformPointCloud in
+ * double) and appended. The gate is sequential and runs on the host; the transform + append run on the device.
+ * The map lives on the device as 16-byte x,y,z,1.0f points in frame order and persists across batches. */
+typedef struct lfx_pose {      /* geometry_msgs/Pose */
+  double position[3];          /* x, y, z */
+  double orientation[4];       /* x, y, z, w */
+} lfx_pose;
+/* poses: one per scan of the last lfx_extract_batch. selected_out (optional, [n_scans]): 1 where the frame was
+ * added. Synchronous. */
+int lfx_map_add_batch(lfx_handle *h, const lfx_pose *poses, int n_poses, uint8_t *selected_out, uint64_t *map_points_out);
+int lfx_map_size(lfx_handle *h, uint64_t *n_points_out);
+int lfx_map_fetch(lfx_handle *h, uint64_t first, uint64_t n_points, float *xyz /* [n_points][4] */);
+int lfx_map_clear(lfx_handle *h);
+/* PoseDiffIsSufficientlySmall (map.hpp:50-60) on two poses: 1 small, 0 not (host arithmetic, exposed for tests). */
+int lfx_pose_diff_is_small(const lfx_pose *pose0, const lfx_pose *pose1, double translation_threshold, double rotation_threshold);
+
 /* ------------------------------------------------------------------ memory helpers */
 /* Pinned host memory so that H2D/D2H run at full PCIe speed. */
 void *lfx_host_alloc(size_t bytes);

@@ -136,6 +136,12 @@ class ConvertResult(C.Structure):
                 ("kept", C.POINTER(C.c_uint32)), ("status", C.POINTER(C.c_uint32))]
 
 
+class Pose(C.Structure):
+    """lfx_pose == geometry_msgs/Pose (orientation x, y, z, w)."""
+
+    _fields_ = [("position", C.c_double * 3), ("orientation", C.c_double * 4)]
+
+
 class ColoredResult(C.Structure):
     _fields_ = [("n_scans", C.c_int), ("d_points", C.c_void_p), ("point_base", C.POINTER(C.c_uint64)),
                 ("counts", C.POINTER(C.c_uint32))]
@@ -225,6 +231,11 @@ def lib() -> C.CDLL:
     L.lfx_color_batch.argtypes = [H, C.POINTER(ColoredResult)]
     L.lfx_fetch_colored.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     L.lfx_topic_layout.argtypes = [C.c_int, C.POINTER(PointFieldC), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.lfx_map_add_batch.argtypes = [H, C.POINTER(Pose), C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.lfx_map_size.argtypes = [H, C.POINTER(C.c_uint64)]
+    L.lfx_map_fetch.argtypes = [H, C.c_uint64, C.c_uint64, C.c_void_p]
+    L.lfx_map_clear.argtypes = [H]
+    L.lfx_pose_diff_is_small.argtypes = [C.POINTER(Pose), C.POINTER(Pose), C.c_double, C.c_double]
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]
     L.lfx_synth_scan_host.argtypes = [C.POINTER(SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
     L.lfx_synth_batch_device.argtypes = [H, C.POINTER(SynthSpec), C.c_uint64, C.c_int, C.c_void_p]

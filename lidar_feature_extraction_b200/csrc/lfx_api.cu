@@ -24,6 +24,7 @@
 #include "lfx_synth.h"
 #include "lfx_convert.cuh"
 #include "lfx_color.cuh"
+#include "lfx_map.cuh"
 
 using namespace lfxk;
 
@@ -112,6 +113,12 @@ struct lfx_handle
   std::vector<uint32_t> colored_counts;
   std::vector<uint64_t> colored_base;
   bool have_colored = false;
+  // mapping accumulate (lfx_map_add_batch)
+  DevBuf<float4> d_map;
+  DevBuf<MapFrame> d_map_frames;
+  uint64_t map_points = 0;
+  bool map_empty = true;
+  double map_prev[12] = {0};
 
   // pinned host staging
   ScanDesc * h_scans = nullptr;
@@ -574,6 +581,7 @@ void lfx_destroy(lfx_handle * h)
   cudaFree(h->d_ring_path.p);
   cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p); cudaFree(h->d_conv_tile_cloud.p);
   cudaFree(h->d_colored.p); cudaFree(h->d_colored_counts.p);
+  cudaFree(h->d_map.p); cudaFree(h->d_map_frames.p);
   for (auto & ev : h->conv_ev) { if (ev) { cudaEventDestroy(ev); } }
   cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
@@ -1370,6 +1378,162 @@ int lfx_topic_layout(int topic, lfx_point_field * fields, uint32_t * n_fields, u
     *n_fields = 4;
     *point_step = 32; // sizeof(pcl::PointXYZRGB)
   }
+  return LFX_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- mapping accumulate
+
+namespace
+{
+
+// tf2::fromMsg(Pose, Isometry3d) = Translation3d(p) * Quaterniond(w, x, y, z), with Eigen's toRotationMatrix
+void pose_matrix(const lfx_pose & p, double * m)
+{
+  const double x = p.orientation[0], y = p.orientation[1], z = p.orientation[2], w = p.orientation[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  m[0] = 1.0 - (tyy + tzz); m[1] = txy - twz; m[2] = txz + twy; m[3] = p.position[0];
+  m[4] = txy + twz; m[5] = 1.0 - (txx + tzz); m[6] = tyz - twx; m[7] = p.position[1];
+  m[8] = txz - twy; m[9] = tyz + twx; m[10] = 1.0 - (txx + tyy); m[11] = p.position[2];
+}
+
+// PoseDiffIsSufficientlySmall, map.hpp:50-60, on row-major 3x4 matrices: d = pose0^-1 * pose1, Quaterniond(d.rotation())
+// by Eigen's matrix -> quaternion assignment, dt.norm() < tt && dq.vec().norm() < rt
+bool pose_diff_small(const double * m0, const double * m1, double tt, double rt)
+{
+  double r0t[3][3], it[3], d[3][3], dt[3];
+  for (int a = 0; a < 3; a++) { for (int b = 0; b < 3; b++) { r0t[a][b] = m0[4 * b + a]; } }
+  for (int a = 0; a < 3; a++) { it[a] = -((r0t[a][0] * m0[3] + r0t[a][1] * m0[7]) + r0t[a][2] * m0[11]); }
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) { d[a][b] = (r0t[a][0] * m1[b] + r0t[a][1] * m1[4 + b]) + r0t[a][2] * m1[8 + b]; }
+    dt[a] = ((r0t[a][0] * m1[3] + r0t[a][1] * m1[7]) + r0t[a][2] * m1[11]) + it[a];
+  }
+  double q[3] = {0.0, 0.0, 0.0};
+  double t = d[0][0] + d[1][1] + d[2][2];
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0);
+    t = 0.5 / t;
+    q[0] = (d[2][1] - d[1][2]) * t; q[1] = (d[0][2] - d[2][0]) * t; q[2] = (d[1][0] - d[0][1]) * t;
+  } else {
+    int i = 0;
+    if (d[1][1] > d[0][0]) { i = 1; }
+    if (d[2][2] > d[i][i]) { i = 2; }
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(d[i][i] - d[j][j] - d[k][k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[j] = (d[j][i] + d[i][j]) * t; q[k] = (d[k][i] + d[i][k]) * t;
+  }
+  const double dt_norm = std::sqrt((dt[0] * dt[0] + dt[1] * dt[1]) + dt[2] * dt[2]);
+  const double dq_norm = std::sqrt((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]);
+  return dt_norm < tt && dq_norm < rt;
+}
+
+// grow-only, contents preserved
+int map_reserve(lfx_handle * h, uint64_t points)
+{
+  if (points <= h->d_map.cap) { return LFX_OK; }
+  const size_t want = (size_t)points + (size_t)points / 2 + 4096;
+  float4 * p = nullptr;
+  LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&p), want * sizeof(float4)));
+  if (h->map_points) { LFX_CUDA(h, cudaMemcpyAsync(p, h->d_map.p, h->map_points * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream)); }
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->d_map.p) { LFX_CUDA(h, cudaFree(h->d_map.p)); }
+  h->d_map.p = p;
+  h->d_map.cap = want;
+  return LFX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lfx_pose_diff_is_small(const lfx_pose * pose0, const lfx_pose * pose1, double translation_threshold, double rotation_threshold)
+{
+  if (!pose0 || !pose1) { return -1; }
+  double m0[12], m1[12];
+  pose_matrix(*pose0, m0);
+  pose_matrix(*pose1, m1);
+  return pose_diff_small(m0, m1, translation_threshold, rotation_threshold) ? 1 : 0;
+}
+
+int lfx_map_add_batch(lfx_handle * h, const lfx_pose * poses, int n_poses, uint8_t * selected_out, uint64_t * map_points_out)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->have_batch) { return fail(h, LFX_E_STATE, "no batch has been extracted"); }
+  if (n_poses != h->n_scans || (n_poses > 0 && !poses)) { return fail(h, LFX_E_BAD_PARAM, "one pose per scan of the last batch is required"); }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  const int ns = h->n_scans;
+  std::vector<uint32_t> offsets((size_t)2 * (ns + 1), 0);
+  if (ns > 0) {
+    LFX_CUDA(h, cudaMemcpyAsync(offsets.data(), h->d_offsets.p, sizeof(uint32_t) * 2 * ((size_t)ns + 1), cudaMemcpyDeviceToHost, h->stream));
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  // MapBuilder::Callback, map.hpp:104-127, frame by frame (translation_threshold 1.0, rotation_threshold 0.1, :92-93)
+  std::vector<MapFrame> frames;
+  uint64_t dst = h->map_points;
+  uint32_t longest = 0;
+  for (int s = 0; s < ns; s++) {
+    if (selected_out) { selected_out[s] = 0; }
+    const uint32_t n = offsets[2 * ((size_t)s + 1)] - offsets[2 * (size_t)s];
+    if (n == 0) { continue; }                                                       // :117-120
+    double m[12];
+    pose_matrix(poses[s], m);
+    if (!h->map_empty && pose_diff_small(h->map_prev, m, 1.0, 0.1)) { continue; }   // :122-128
+    MapFrame f;
+    memcpy(f.m, m, sizeof(m));
+    f.dst = dst; f.src = offsets[2 * (size_t)s]; f.n = n;
+    frames.push_back(f);
+    dst += n;
+    longest = std::max(longest, n);
+    memcpy(h->map_prev, m, sizeof(m));                                              // :131
+    h->map_empty = false;
+    if (selected_out) { selected_out[s] = 1; }
+  }
+  if (!frames.empty()) {
+    int rc;
+    if ((rc = map_reserve(h, dst))) { return rc; }
+    if ((rc = ensure(h, h->d_map_frames, frames.size(), nullptr))) { return rc; }
+    LFX_CUDA(h, cudaMemcpyAsync(h->d_map_frames.p, frames.data(), sizeof(MapFrame) * frames.size(), cudaMemcpyHostToDevice, h->stream));
+    const unsigned gy = (unsigned)std::min<uint32_t>(std::max<uint32_t>((longest + MAP_THREADS * 4 - 1) / (MAP_THREADS * 4), 1u), 64u);
+    for (size_t f0 = 0; f0 < frames.size(); f0 += 1u << 30) {
+      const unsigned gx = (unsigned)std::min<size_t>(frames.size() - f0, (size_t)1u << 30);
+      k_map_transform_add<<<dim3(gx, gy), MAP_THREADS, 0, h->stream>>>(h->d_map_frames.p + f0, h->d_edge.p, h->d_map.p);
+      LFX_CUDA(h, cudaGetLastError());
+      h->launches += 1;
+    }
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));   // `frames` is host memory of this call
+    h->map_points = dst;
+  }
+  if (map_points_out) { *map_points_out = h->map_points; }
+  return LFX_OK;
+}
+
+int lfx_map_size(lfx_handle * h, uint64_t * n_points_out)
+{
+  if (!h || !n_points_out) { return LFX_E_BAD_PARAM; }
+  *n_points_out = h->map_points;
+  return LFX_OK;
+}
+
+int lfx_map_fetch(lfx_handle * h, uint64_t first, uint64_t n_points, float * xyz)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (first + n_points > h->map_points || (n_points > 0 && !xyz)) { return fail(h, LFX_E_BAD_PARAM, "range outside the map"); }
+  if (n_points == 0) { return LFX_OK; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LFX_CUDA(h, cudaMemcpyAsync(xyz, h->d_map.p + first, n_points * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+int lfx_map_clear(lfx_handle * h)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  h->map_points = 0;
+  h->map_empty = true;
   return LFX_OK;
 }
 
