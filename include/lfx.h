@@ -304,6 +304,13 @@ int lfx_map_add_batch(lfx_handle *h, const lfx_pose *poses, int n_poses, uint8_t
 int lfx_map_size(lfx_handle *h, uint64_t *n_points_out);
 int lfx_map_fetch(lfx_handle *h, uint64_t first, uint64_t n_points, float *xyz /* [n_points][4] */);
 int lfx_map_clear(lfx_handle *h);
+/* The gate alone, on the host (no device work): MapBuilder::Callback's decisions (map.hpp:117-131) for a sequence of
+ * frames given their poses and scan_edge sizes. *map_empty_io / *prev_io carry the builder's state in and out
+ * (prev_io is only read when *map_empty_io == 0). selected: [n] 0/1. A rank of the sharded driver runs it over the
+ * frames before its shard (sizes from the count all-gather) and installs the result with lfx_map_set_state, so that
+ * its part of the map equals the corresponding part of the sequential map. */
+int lfx_map_gate(const lfx_pose *poses, const uint32_t *n_edge, int n, int *map_empty_io, lfx_pose *prev_io, uint8_t *selected);
+int lfx_map_set_state(lfx_handle *h, int map_empty, const lfx_pose *prev);
 /* PoseDiffIsSufficientlySmall (map.hpp:50-60) on two poses: 1 small, 0 not (host arithmetic, exposed for tests). */
 int lfx_pose_diff_is_small(const lfx_pose *pose0, const lfx_pose *pose1, double translation_threshold, double rotation_threshold);
 

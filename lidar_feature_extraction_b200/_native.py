@@ -235,6 +235,8 @@ def lib() -> C.CDLL:
     L.lfx_map_size.argtypes = [H, C.POINTER(C.c_uint64)]
     L.lfx_map_fetch.argtypes = [H, C.c_uint64, C.c_uint64, C.c_void_p]
     L.lfx_map_clear.argtypes = [H]
+    L.lfx_map_gate.argtypes = [C.POINTER(Pose), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(Pose), C.c_void_p]
+    L.lfx_map_set_state.argtypes = [H, C.c_int, C.POINTER(Pose)]
     L.lfx_pose_diff_is_small.argtypes = [C.POINTER(Pose), C.POINTER(Pose), C.c_double, C.c_double]
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]
     L.lfx_synth_scan_host.argtypes = [C.POINTER(SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]

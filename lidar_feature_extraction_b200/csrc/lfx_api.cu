@@ -1459,6 +1459,34 @@ int lfx_pose_diff_is_small(const lfx_pose * pose0, const lfx_pose * pose1, doubl
   return pose_diff_small(m0, m1, translation_threshold, rotation_threshold) ? 1 : 0;
 }
 
+int lfx_map_gate(const lfx_pose * poses, const uint32_t * n_edge, int n, int * map_empty_io, lfx_pose * prev_io, uint8_t * selected)
+{
+  if (n < 0 || (n > 0 && (!poses || !n_edge)) || !map_empty_io || !prev_io) { return LFX_E_BAD_PARAM; }
+  double prev[12] = {0}, m[12];
+  bool empty = *map_empty_io != 0;
+  if (!empty) { pose_matrix(*prev_io, prev); }
+  for (int i = 0; i < n; i++) {
+    if (selected) { selected[i] = 0; }
+    if (n_edge[i] == 0) { continue; }
+    pose_matrix(poses[i], m);
+    if (!empty && pose_diff_small(prev, m, 1.0, 0.1)) { continue; }
+    memcpy(prev, m, sizeof(m));
+    *prev_io = poses[i];
+    empty = false;
+    if (selected) { selected[i] = 1; }
+  }
+  *map_empty_io = empty ? 1 : 0;
+  return LFX_OK;
+}
+
+int lfx_map_set_state(lfx_handle * h, int map_empty, const lfx_pose * prev)
+{
+  if (!h || (!map_empty && !prev)) { return LFX_E_BAD_PARAM; }
+  h->map_empty = map_empty != 0;
+  if (!h->map_empty) { pose_matrix(*prev, h->map_prev); }
+  return LFX_OK;
+}
+
 int lfx_map_add_batch(lfx_handle * h, const lfx_pose * poses, int n_poses, uint8_t * selected_out, uint64_t * map_points_out)
 {
   if (!h) { return LFX_E_BAD_PARAM; }

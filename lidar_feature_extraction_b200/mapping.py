@@ -29,6 +29,23 @@ def pose_diff_is_sufficiently_small(pose0: N.Pose, pose1: N.Pose, translation_th
     return N.lib().lfx_pose_diff_is_small(C.byref(pose0), C.byref(pose1), translation_threshold, rotation_threshold) == 1
 
 
+def gate_frames(poses: Sequence[N.Pose], n_edge, map_empty: bool = True, prev: N.Pose | None = None):
+    """MapBuilder::Callback's decisions for a frame sequence (lfx_map_gate, host only).
+    Returns (selected bool array, map_empty, prev pose)."""
+    n = len(poses)
+    arr = (N.Pose * max(n, 1))(*poses)
+    sizes = np.ascontiguousarray(n_edge, np.uint32)
+    sel = np.zeros(n, np.uint8)
+    empty = C.c_int(1 if map_empty else 0)
+    p = N.Pose()
+    if prev is not None:
+        C.memmove(C.byref(p), C.byref(prev), C.sizeof(N.Pose))
+    rc = N.lib().lfx_map_gate(arr, sizes.ctypes.data, n, C.byref(empty), C.byref(p), sel.ctypes.data)
+    if rc != N.LFX_OK:
+        raise ValueError("lfx_map_gate: bad arguments")
+    return sel.astype(bool), bool(empty.value), p
+
+
 class MapBuilder:
     def __init__(self, extraction: FeatureExtraction):
         self.extraction = extraction
@@ -58,6 +75,10 @@ class MapBuilder:
         out = np.zeros((len(self), 4), np.float32)
         self._check(self._lib.lfx_map_fetch(self.extraction.handle, 0, out.shape[0], out.ctypes.data))
         return out
+
+    def set_state(self, map_empty: bool, prev: N.Pose | None = None):
+        """Install the gate state (sharded driver: the state after the frames before this rank's shard)."""
+        self._check(self._lib.lfx_map_set_state(self.extraction.handle, 1 if map_empty else 0, C.byref(prev) if prev is not None else None))
 
     def clear(self):
         self._check(self._lib.lfx_map_clear(self.extraction.handle))

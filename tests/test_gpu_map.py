@@ -65,3 +65,33 @@ def test_map_of_reference_test_vector():
         shifted = e.copy()
         shifted[:, 0] = (e[:, 0].astype(np.float64) + 3.0).astype(np.float32)
         assert np.array_equal(m[len(e):], shifted)
+
+
+def test_sharded_map_equals_the_sequential_map():
+    """Two 'ranks' (two handles here) own frames [0, 9) and [9, 16): each installs the gate state of the frames
+    before its shard (lfx_map_gate over the gathered sizes) and builds its part; the parts concatenate to the map
+    one sequential MapBuilder produces."""
+    from lidar_feature_extraction_b200 import FeatureExtraction, MapBuilder, make_pose, synth
+    from lidar_feature_extraction_b200.mapping import gate_frames
+
+    rng = np.random.default_rng(2)
+    sp = synth.spec("vlp16")
+    n, cut = 16, 9
+    clouds = [synth.scan_host(sp, f) for f in range(n)]
+    poses = [make_pose(*p) for p in _trajectory(n, rng)]
+    with FeatureExtraction() as fe:
+        mb = MapBuilder(fe)
+        out = fe.extract_batch(clouds, fetch_points=False)
+        sizes = out.counts[:, 0].copy()
+        mb.add_batch(poses)
+        whole = mb.points()
+    parts = []
+    for lo, hi in ((0, cut), (cut, n)):
+        with FeatureExtraction() as fe:
+            mb = MapBuilder(fe)
+            _, empty, prev = gate_frames(poses[:lo], sizes[:lo])
+            mb.set_state(empty, None if empty else prev)
+            fe.extract_batch(clouds[lo:hi], fetch_points=False)
+            mb.add_batch(poses[lo:hi])
+            parts.append(mb.points())
+    assert np.array_equal(np.concatenate(parts).view(np.uint32), whole.view(np.uint32))

@@ -45,3 +45,25 @@ def test_random_pose_pairs_agree_with_the_oracle():
         assert small(make_pose(t0, q0), make_pose(t1, q1), 1.0, 0.1) == want
         n_small += want
     assert 100 < n_small < 1900
+
+
+def test_gate_sequence_and_shard_state_agree_with_the_oracle():
+    """lfx_map_gate over a whole sequence == the oracle's MapBuilder::Callback loop, and gating a shard after
+    installing the state of its prefix gives the same decisions (what a rank of the sharded driver does)."""
+    from lidar_feature_extraction_b200 import make_pose
+    from lidar_feature_extraction_b200.mapping import gate_frames
+
+    rng = np.random.default_rng(4)
+    n = 400
+    pos = np.cumsum(rng.choice([0.0, 0.3, 0.6, 1.5], size=(n, 1)) * rng.normal(size=(n, 3)), axis=0)
+    yaw = np.cumsum(rng.choice([0.0, 0.02, 0.3], size=n))
+    quats = [np.array([0, 0, np.sin(a / 2), np.cos(a / 2)]) for a in yaw]
+    sizes = rng.choice([0, 7, 300], size=n, p=[0.1, 0.45, 0.45])
+    poses = [make_pose(p, q) for p, q in zip(pos, quats)]
+    want, _, _ = mo.gate_frames([mo.pose_to_matrix(p, q) for p, q in zip(pos, quats)], sizes)
+    got, empty, _ = gate_frames(poses, sizes)
+    assert got.tolist() == want.tolist() and not empty and 20 < got.sum() < n
+    for lo in (0, 1, 137, 399):
+        _, e0, p0 = gate_frames(poses[:lo], sizes[:lo])
+        tail, _, _ = gate_frames(poses[lo:], sizes[lo:], map_empty=e0, prev=p0)
+        assert tail.tolist() == want[lo:].tolist()
