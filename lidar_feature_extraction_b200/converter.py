@@ -59,17 +59,23 @@ class PointTypeConverter:
         does not raise for per-cloud failures - see ``status_of`` / ``fetch``."""
         h = self.extraction.handle
         keep, raws = [], []
+        field_cache = {}   # clouds of one driver share their field table: marshal it once
         for m in msgs:
-            names = [f.name.encode() for f in m.fields]
-            arr = (N.PointFieldC * max(len(m.fields), 1))(*[N.PointFieldC(nm, f.offset, f.datatype, f.count) for nm, f in zip(names, m.fields)])
+            key = id(m.fields)
+            hit = field_cache.get(key)
+            if hit is None:
+                names = [f.name.encode() for f in m.fields]
+                arr = (N.PointFieldC * max(len(m.fields), 1))(*[N.PointFieldC(nm, f.offset, f.datatype, f.count) for nm, f in zip(names, m.fields)])
+                hit = field_cache[key] = (names, arr, len(m.fields))
+            names, arr, nf = hit
             data = m.data
             if _is_cuda_tensor(data):
                 ptr, nbytes, mem = data.data_ptr(), data.numel() * data.element_size(), N.LFX_MEM_DEVICE
             else:
                 data = np.ascontiguousarray(np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data).reshape(-1).view(np.uint8)
                 ptr, nbytes, mem = data.ctypes.data, data.nbytes, N.LFX_MEM_HOST
-            keep.append((names, arr, data))
-            raws.append(N.RawCloud(ptr, nbytes, m.point_step, arr, len(m.fields), 1 if m.is_bigendian else 0, mem))
+            keep.append((names, arr, data, m.fields))
+            raws.append(N.RawCloud(ptr, nbytes, m.point_step, arr, nf, 1 if m.is_bigendian else 0, mem))
         res = N.ConvertResult()
         carr = (N.RawCloud * max(len(raws), 1))(*raws)
         rc = self._lib.lfx_convert_batch(h, carr, len(raws), C.byref(res))

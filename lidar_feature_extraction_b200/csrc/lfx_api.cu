@@ -1145,6 +1145,9 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
   std::vector<uint8_t> needs_six((size_t)n_clouds, 0), ring_float((size_t)n_clouds, 0), active((size_t)n_clouds, 0);
   std::vector<uint32_t> tile_cloud;
   bool all_fast = true;
+  bool have_plan = false, plan_six = false, plan_rf = false, plan_aligned = false;
+  lfx_raw_cloud plan_src{};
+  ConvCloud plan_cc{};
   uint64_t points = 0, host_bytes = 0;
   uint32_t tiles = 0, max_step = 1;
   for (int c = 0; c < n_clouds; c++) {
@@ -1160,7 +1163,21 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
     if (n > 0xFFFFFFFFull) { return fail(h, LFX_E_BAD_PARAM, "more than 2^32 - 1 points in one cloud"); }
     if (n > 0 && !rc.data) { return fail(h, LFX_E_BAD_PARAM, "cloud without data"); }
     bool six = false, rf = false;
-    const uint32_t st = conv_make_plan(rc, k, six, rf);
+    uint32_t st;
+    // clouds of one driver share field table, point_step and byte order: resolve the plan once per batch
+    const bool same_plan = have_plan && rc.fields == plan_src.fields && rc.n_fields == plan_src.n_fields && rc.point_step == plan_src.point_step &&
+                           rc.is_bigendian == plan_src.is_bigendian && rc.memory == plan_src.memory && n > 0 &&
+                           (rc.memory == LFX_MEM_HOST || reinterpret_cast<uintptr_t>(rc.data) % 16 == 0) == plan_aligned;
+    if (same_plan) {
+      k = plan_cc; six = plan_six; rf = plan_rf; st = LFX_CONVERT_OK;
+      k.tile_base = tiles;
+    } else {
+      st = conv_make_plan(rc, k, six, rf);
+      if (st == LFX_CONVERT_OK && n > 0) {
+        have_plan = true; plan_src = rc; plan_cc = k; plan_six = six; plan_rf = rf;
+        plan_aligned = rc.memory == LFX_MEM_HOST || reinterpret_cast<uintptr_t>(rc.data) % 16 == 0;
+      }
+    }
     h->conv_status[(size_t)c] = st;
     if (st != LFX_CONVERT_OK || n == 0) { continue; }
     needs_six[(size_t)c] = six; ring_float[(size_t)c] = rf; active[(size_t)c] = 1;
