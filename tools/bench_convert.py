@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--scans", type=int, default=1250)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--chain", action="store_true", help="also time raw clouds -> converter -> extraction on the device")
     args = ap.parse_args()
     import torch
 
@@ -87,6 +88,28 @@ def main():
                                    "points_per_sec_kernel": n / (kernel_ms * 1e-3)},
                       "cpu_baseline": {"value": sample.shape[0] * per / cpu_s, "unit": "points/s", "cores": 1, "kind": "port",
                                        "sample": f"{sample.shape[0]} clouds, numpy port of convert.py"}}))
+    if args.chain:
+        # /points_raw -> features without leaving the device: the converted clouds (3 % of the returns removed, so rings
+        # are ragged and the scans take the bucketing + indexed sector path) feed lfx_extract_batch directly
+        def chain_step():
+            conv.convert_batch(msgs)
+            fe.extract_views(fe.view_array([conv.view(s) for s in range(args.scans)]))
+        for _ in range(2):
+            chain_step()
+        fe.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            chain_step()
+        fe.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        fe.set_stage_timing(True)
+        chain_step()
+        fe.synchronize()
+        st = fe.last_stage_ms()
+        print(json.dumps({"metric": "raw_points_per_sec_converted_and_extracted", "value": n / (ms * 1e-3), "unit": "points/s",
+                          "ms_per_step": ms, "convert_kernel_ms": kernel_ms,
+                          "extract_stage_ms": dict(zip(["probe", "sectors", "bucketing", "sectors_indexed", "rings", "pack"], [round(v, 3) for v in st])),
+                          "paths": fe.batch_stats()}))
     conv.close()
     fe.close()
 
