@@ -109,11 +109,13 @@ def test_sparse_ring_ids_and_ring_datatypes(oracle):
     assert stats["general_scans"] == 0 and sum(stats["fast_rings"]) == 5
     x, y, z, _, ring = (np.ascontiguousarray(a) for a in synth.fields(base))
     want = oracle.extract_scan(base, oracle_params(ob, hp))
-    # (point_step, x offset, ring offset, ring datatype): ring in the chunk after x,y,z,w / inside it / before it /
-    # far away from it (the sector kernel stages the aligned word holding the field; the ABI requires a naturally
-    # aligned ring field, so it never straddles two words)
-    for step, ox, oring, rdt, npdt, fast in ((48, 16, 44, 6, np.uint32, True), (32, 0, 13, 2, np.uint8, True),
-                                             (64, 32, 18, 4, np.uint16, True), (64, 32, 2, 4, np.uint16, True)):
+    # (point_step, x offset, ring offset, ring datatype, regular path?): the regular (strided) path fetches whole
+    # 32-byte points, so it needs 32-byte aligned records with the ring word at +20 from x (the deployed layout);
+    # every other layout is bucketed and runs on the indexed sector path - same results
+    for step, ox, oring, rdt, npdt, fast in ((32, 0, 20, 4, np.uint16, True), (64, 32, 52, 6, np.uint32, True),
+                                             (32, 0, 21, 2, np.uint8, True), (48, 16, 44, 6, np.uint32, False),
+                                             (32, 0, 13, 2, np.uint8, False), (64, 32, 18, 4, np.uint16, False),
+                                             (64, 32, 2, 4, np.uint16, False)):
         buf = np.zeros((len(x), step), np.uint8)
         for k, a in enumerate((x, y, z)):
             buf[:, ox + 4 * k: ox + 4 * k + 4] = a.view(np.uint8).reshape(-1, 4)
