@@ -165,5 +165,35 @@ private:
   lfx_handle * h_;
 };
 
+// The mapping package's accumulate step (mapping/include/lidar_feature_mapping/map.hpp:62-145) for the batched
+// offline sequence: AddBatch(poses) does for every frame of the last extracted batch what MapBuilder::Callback does
+// for one (scan_edge, pose) pair. The map stays on the device; Points() copies it out (x,y,z,1.0f per point).
+class MapBuilder
+{
+public:
+  explicit MapBuilder(FeatureExtraction & fe) : h_(fe.handle()) {}
+  std::vector<uint8_t> AddBatch(const std::vector<lfx_pose> & poses)   // 1 where the frame was added
+  {
+    std::vector<uint8_t> selected(poses.size());
+    uint64_t n = 0;
+    Check(lfx_map_add_batch(h_, poses.data(), static_cast<int>(poses.size()), selected.data(), &n));
+    return selected;
+  }
+  bool IsEmpty() { return Size() == 0; }
+  uint64_t Size() { uint64_t n = 0; Check(lfx_map_size(h_, &n)); return n; }
+  std::vector<float> Points()
+  {
+    std::vector<float> xyz(static_cast<size_t>(Size()) * 4);
+    Check(lfx_map_fetch(h_, 0, xyz.size() / 4, xyz.data()));
+    return xyz;
+  }
+  // sharded driver: the gate state after the frames before this rank's shard (lfx_map_gate over the gathered sizes)
+  void SetState(bool map_empty, const lfx_pose * prev) { Check(lfx_map_set_state(h_, map_empty ? 1 : 0, prev)); }
+
+private:
+  void Check(int rc) { if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); } }
+  lfx_handle * h_;
+};
+
 }  // namespace lfx
 #endif  // LFX_HPP_
