@@ -281,7 +281,12 @@ def main():
     first_frame, last_frame = sharding.shard_range(n_frames, rank, world)  # rank g owns [g*F/G, (g+1)*F/G)
     assert last_frame - first_frame == scans_per_gpu
 
-    stream = torch.cuda.current_stream(dev)
+    # one explicit stream for everything that is timed: the library launches on it, NCCL (torch's current stream)
+    # runs on it and the timing events are recorded on it. (torch's default stream has handle 0, which the C ABI
+    # reads as "create your own stream": events on the default stream would then not bracket the kernels.)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     fe = FeatureExtraction(HyperParameters(), device=local_rank, stream=stream.cuda_stream,
                            max_rings=max(128, sp.n_rings))
     lib = N.lib()
@@ -326,16 +331,22 @@ def main():
     sampler = ClockSampler(local_rank, uuid)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     sharded.join()
     e1.record(stream)
     torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
+    # the events sit on the stream every kernel of the step is launched on, so the host clock around the same
+    # region (synchronize included) can only be slightly larger; anything else means the events missed work
+    if not (0.8 * wall_ms - 1.0 <= ms_total <= wall_ms * 1.001 + 0.05):
+        print(f"warning: rank {rank}: event time {ms_total:.3f} ms vs host clock {wall_ms:.3f} ms", file=sys.stderr)
     launches = fe.kernel_launches - launches0
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -349,14 +360,20 @@ def main():
     lib.lfx_fetch_counts(fe.handle, counts.ctypes.data, offsets.ctypes.data)
     n_feat = int(offsets[-1, 0]) + int(offsets[-1, 1])
     alg_bytes = 32 * n_points + n_points + 16 * n_feat + 8 * scans_per_gpu  # SURVEY.md 8(d) / BASELINE.md 4
-    fe.set_stage_timing(True)
-    stage = []
-    for _ in range(max(3, min(args.steps, 10))):
-        fe.extract_views(dev_views, keep=d_in)
-        fe.synchronize()
-        stage.append(fe.last_stage_ms())
-    fe.set_stage_timing(False)
-    stage = np.array(stage[1:]) if len(stage) > 1 else np.array(stage)
+    # (a) as in the timed region: the batch runs as its CUDA graph, steps back to back, the stage events are
+    #     event-record nodes of that graph; (b) eager launches with a synchronize between steps, for comparison
+    def stage_loop(mode, sync):
+        fe.set_stage_timing(mode)
+        rows = []
+        for _ in range(max(3, min(args.steps, 10)) + 1):
+            fe.extract_views(dev_views, keep=d_in)
+            if sync:
+                fe.synchronize()
+            rows.append(fe.last_stage_ms())
+        fe.set_stage_timing(False)
+        return np.array(rows[1:])
+    stage = stage_loop(2, False)
+    stage_eager = stage_loop(1, True)
     # k_extract_sectors: launches on regular scans (stage 1) + launches on bucketed rings (stage 3); on a given
     # workload one instantiation holds (nearly) the whole batch
     ring_ms = float((stage[:, 1] + stage[:, 3]).mean())
@@ -377,6 +394,8 @@ def main():
                 "stage_ms": {"probe": float(stage[:, 0].mean()), "sectors": float(stage[:, 1].mean()),
                              "bucketing": float(stage[:, 2].mean()), "sectors_indexed": float(stage[:, 3].mean()),
                              "rings": float(stage[:, 4].mean()), "pack": float(stage[:, 5].mean())},
+                "stage_ms_how": "event-record nodes inside the batch's CUDA graph, steps back to back as in the timed region",
+                "kernel_ms_eager": float((stage_eager[:, 1] + stage_eager[:, 3]).mean()),
                 "paths": fe.batch_stats(),
                 "pipeline_frac": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
 
@@ -445,7 +464,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "sensor": sensor, "rings": sp.n_rings, "cols": sp.n_cols,
                        "scans_per_gpu": scans_per_gpu, "points_per_gpu": n_points, "params": "compiled defaults (hyper_parameter.hpp:35-43)",

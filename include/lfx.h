@@ -323,13 +323,20 @@ int lfx_device_free(lfx_handle *h, void *p);
 int lfx_memcpy_h2d(lfx_handle *h, void *dst_device, const void *src_host, size_t bytes);
 int lfx_memcpy_d2h(lfx_handle *h, void *dst_host, const void *src_device, size_t bytes);
 
+/* The cudaStream_t every kernel and copy of this handle is enqueued on (the one given in lfx_options, or the
+ * stream the handle created). A caller that chains its own work (the sharded driver's NCCL all-gather of the
+ * per-scan counts, timing events) must enqueue it on this stream or order against it. */
+void *lfx_stream(const lfx_handle *h);
+
 /* ------------------------------------------------------------------ instrumentation */
 /* Kernels launched / graph launches issued by this handle so far (bench.py's gpu_launches). */
 uint64_t lfx_kernel_launch_count(const lfx_handle *h);
 /* Device time of the last batch's stages, measured with CUDA events on the handle's stream:
  * ms[0]=layout probe, ms[1]=sector kernel on regular scans, ms[2]=ring bucketing of the other scans (list +
  * hist + plan + scatter + ring probe), ms[3]=sector kernel on bucketed rings, ms[4]=per-ring (sort) kernel,
- * ms[5]=pack. Only when timing was enabled. */
+ * ms[5]=pack. Only when timing was enabled. enabled = 1: the batch is launched kernel by kernel with event records
+ * in between (no graph); enabled = 2: the batch runs as its CUDA graph, as in production, with the events as
+ * event-record nodes of that graph (what bench.py reports); 0: off. */
 #define LFX_N_STAGES 6
 int lfx_set_stage_timing(lfx_handle *h, int enabled);
 int lfx_last_stage_ms(lfx_handle *h, float *ms /* [LFX_N_STAGES] */);

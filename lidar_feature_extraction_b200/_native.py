@@ -202,6 +202,8 @@ def lib() -> C.CDLL:
     L.lfx_last_error.restype = C.c_char_p
     L.lfx_get_params.argtypes = [H, C.POINTER(Params)]
     L.lfx_device.argtypes = [H]
+    L.lfx_stream.argtypes = [H]
+    L.lfx_stream.restype = C.c_void_p
     L.lfx_extract_batch.argtypes = [H, C.POINTER(CloudView), C.c_int, C.POINTER(BatchResult)]
     L.lfx_synchronize.argtypes = [H]
     L.lfx_batch_status.argtypes = [H]

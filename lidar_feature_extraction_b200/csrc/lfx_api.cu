@@ -44,7 +44,13 @@ struct GraphKey
 {
   int n_scans;
   uint32_t n_tiles;
-  bool operator<(const GraphKey & o) const { return n_scans != o.n_scans ? n_scans < o.n_scans : n_tiles < o.n_tiles; }
+  bool timed;   // the graph carries event-record nodes around the stages (lfx_set_stage_timing(h, 2))
+  bool operator<(const GraphKey & o) const
+  {
+    if (n_scans != o.n_scans) { return n_scans < o.n_scans; }
+    if (n_tiles != o.n_tiles) { return n_tiles < o.n_tiles; }
+    return timed < o.timed;
+  }
 };
 
 }  // namespace
@@ -140,6 +146,7 @@ struct lfx_handle
   bool have_batch = false;
 
   bool timing = false;
+  bool timing_in_graph = false;   // stage events as external event-record nodes of the captured graph
   cudaEvent_t ev[LFX_N_STAGES + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have_timing = false;
 };
@@ -265,11 +272,14 @@ int validate_params(const lfx_params & p, std::string & why)
 }
 
 // ---- the batch pipeline (enqueued on h->stream; also the body of the captured graph)
-int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_events)
+int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_events, bool capturing = false)
 {
+  // inside a stream capture a plain cudaEventRecord only marks a dependency; the External flag makes it a real
+  // event-record node that is timestamped on every launch of the graph
+  const unsigned ev_flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
   const int max_rings = h->opt.max_rings;
   LFX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * C_COUNT, h->stream));
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[0], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[0], h->stream, ev_flags)); }
   // ---- fast path: layout probe, then one warp per ring-sector
   ProbeArgs pa;
   pa.scans = h->d_scans.p;
@@ -282,7 +292,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   pa.B = h->params.n_blocks;
   pa.enabled = h->fast_enabled ? 1 : 0;
   k_probe_layout<<<n_scans, PROBE_THREADS, sizeof(uint32_t) * (3 * max_rings + 1), h->stream>>>(pa);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[1], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[1], h->stream, ev_flags)); }
   if (h->fast_enabled) {
     for (int c = 0; c < N_FAST_K; c++) {
       SectorArgs sa;
@@ -305,7 +315,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       h->sector_kernel[c]<<<h->sector_grid[c], sector_warps(fast_k(c), false) * 32, h->sector_smem[c], h->stream>>>(sa);
     }
   }
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[2], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[2], h->stream, ev_flags)); }
   // ---- general path for the scans flagged by the probe or by a failed check of the sector kernel
   k_general_list<<<1, 1024, 0, h->stream>>>(h->d_scans.p, n_scans, h->d_scan_flags.p, h->d_gen_scan.p, h->d_gen_tile_base.p,
                                             h->d_tile_owner.p, h->d_counters);
@@ -339,7 +349,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   rp.B = h->params.n_blocks;
   rp.enabled = h->fast_enabled ? 1 : 0;
   k_probe_rings<<<n_scans, PROBE_THREADS, sizeof(uint32_t) * 3 * max_rings, h->stream>>>(rp);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[3], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[3], h->stream, ev_flags)); }
   if (h->fast_enabled) {
     for (int c = 0; c < N_FAST_K; c++) {
       SectorArgs sa;
@@ -362,7 +372,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       h->sector_kernel[N_FAST_K + c]<<<h->sector_grid[N_FAST_K + c], sector_warps(fast_k(c), true) * 32, h->sector_smem[N_FAST_K + c], h->stream>>>(sa);
     }
   }
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[4], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[4], h->stream, ev_flags)); }
   RingArgs ra;
   ra.scans = h->d_scans.p;
   ra.idx = h->d_idx.p;
@@ -380,7 +390,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   ra.force_order_path = h->opt.force_order_path;
   ra.prm = h->dev;
   h->ring_kernel<<<h->ring_grid, h->ring_threads, h->ring_smem, h->stream>>>(ra);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[5], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[5], h->stream, ev_flags)); }
   // ---- packing
   k_feat_offsets_a<<<n_scans, 128, 0, h->stream>>>(h->d_rings.p, h->d_ring_featoff.p, h->d_counts.p, max_rings);
   k_feat_offsets_b<<<1, 1024, 0, h->stream>>>(h->d_counts.p, h->d_offsets.p, n_scans);
@@ -402,7 +412,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   k_pack_copy<<<h->pack_grid, 256, 0, h->stream>>>(
     h->d_work.p, h->d_counters, h->d_scans.p, h->d_rings.p, h->d_ring_featoff.p, h->d_offsets.p, h->d_stage.p,
     h->d_edge.p, h->d_surface.p, max_rings);
-  if (with_events) { LFX_CUDA(h, cudaEventRecord(h->ev[6], h->stream)); }
+  if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[6], h->stream, ev_flags)); }
   LFX_CUDA(h, cudaGetLastError());
   return LFX_OK;
 }
@@ -599,6 +609,8 @@ int lfx_get_params(const lfx_handle * h, lfx_params * out)
 
 int lfx_device(const lfx_handle * h) { return h ? h->device : -1; }
 
+void * lfx_stream(const lfx_handle * h) { return h ? reinterpret_cast<void *>(h->stream) : nullptr; }
+
 int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans, lfx_batch_result * out)
 {
   if (!h) { return LFX_E_BAD_PARAM; }
@@ -742,14 +754,15 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
   h->total_points = total_points;
   h->total_tiles = (uint32_t)total_tiles;
   if (n_scans > 0) {
-    const bool use_graph = h->opt.use_graph >= 0 && !h->timing;
+    const bool timed_graph = h->timing && h->timing_in_graph;
+    const bool use_graph = h->opt.use_graph >= 0 && (!h->timing || timed_graph);
     if (use_graph) {
-      const GraphKey key{n_scans, (uint32_t)total_tiles};
+      const GraphKey key{n_scans, (uint32_t)total_tiles, timed_graph};
       auto it = h->graphs.find(key);
       if (it == h->graphs.end()) {
         cudaGraph_t g = nullptr;
         LFX_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, false);
+        rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, timed_graph, true);
         cudaError_t e = cudaStreamEndCapture(h->stream, &g);
         if (rc) { if (g) { cudaGraphDestroy(g); } return rc; }
         if (e != cudaSuccess) { return fail(h, LFX_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); }
@@ -761,6 +774,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
         it = h->graphs.emplace(key, ge).first;
       }
       LFX_CUDA(h, cudaGraphLaunch(it->second, h->stream));
+      h->have_timing = timed_graph;
     } else {
       if ((rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, h->timing))) { return rc; }
       h->have_timing = h->timing;
@@ -967,6 +981,7 @@ int lfx_set_stage_timing(lfx_handle * h, int enabled)
 {
   if (!h) { return LFX_E_BAD_PARAM; }
   h->timing = enabled != 0;
+  h->timing_in_graph = enabled == 2;
   return LFX_OK;
 }
 

@@ -201,6 +201,11 @@ class FeatureExtraction:
         return self._h
 
     @property
+    def stream(self) -> int:
+        """cudaStream_t (as an integer) every kernel of this handle runs on: the one passed in, else the handle's own."""
+        return int(self._lib.lfx_stream(self._h) or 0)
+
+    @property
     def kernel_launches(self) -> int:
         return int(self._lib.lfx_kernel_launch_count(self._h))
 
@@ -356,8 +361,10 @@ class FeatureExtraction:
                 "indexed_rings": list(st.indexed_rings)}
 
     # -- stage timing
-    def set_stage_timing(self, enabled: bool):
-        self._check(self._lib.lfx_set_stage_timing(self._h, int(enabled)))
+    def set_stage_timing(self, enabled, in_graph: bool = False):
+        """enabled: False/0 off, True/1 eager launches with events, 2 (or in_graph=True) events inside the graph."""
+        mode = 2 if (enabled and in_graph) else int(enabled)
+        self._check(self._lib.lfx_set_stage_timing(self._h, mode))
 
     def last_stage_ms(self):
         ms = (C.c_float * 6)()   # LFX_N_STAGES

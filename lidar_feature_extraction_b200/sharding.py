@@ -104,6 +104,16 @@ class ShardedExtraction:
         self._slots = [None, None]
         self._done = [None, None]
         self._k = 0
+        self._main = None
+
+    def _extraction_stream(self):
+        """torch view of the stream the handle launches on: the gather is enqueued THERE (not on whatever torch's
+        current stream happens to be), so it is ordered after the batch that writes the counts."""
+        import torch
+
+        if self._main is None:
+            self._main = torch.cuda.ExternalStream(self.fe.stream, device=self.device)
+        return self._main
 
     def step(self, views, keep=None):
         import torch
@@ -113,6 +123,12 @@ class ShardedExtraction:
         if self.world == 1:
             self.counts_all = cnt
             return res
+        with torch.cuda.stream(self._extraction_stream()):
+            return self._step_gather(res, cnt)
+
+    def _step_gather(self, res, cnt):
+        import torch
+
         if not self.overlap:
             width = max(shard_sizes(self.n_frames, self.world))
             if self._recv is None or self._recv.shape[0] != self.world * width:
@@ -143,8 +159,9 @@ class ShardedExtraction:
         import torch
 
         if self._side is not None:
-            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._extraction_stream().wait_stream(self._side)
 
     def offsets(self) -> np.ndarray:
         self.join()
+        self.fe.synchronize()      # the counts (and the gather, enqueued on the same stream) are complete
         return global_offsets(self.counts_all.cpu().numpy())

@@ -42,3 +42,26 @@ def test_hdl64_tunnel_covers_every_label(oracle):
         out = fe.extract_batch(clouds)
     hist = np.bincount(out.labels, minlength=256)
     assert (hist[:8] > 0).all(), hist[:8]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_stage_timing_modes_leave_results_unchanged(oracle, mode):
+    """lfx_set_stage_timing: 1 = eager launches with events, 2 = event-record nodes inside the batch's CUDA graph
+    (what bench.py's roofline uses). Either way the batch result is the oracle's and every stage time is >= 0."""
+    from lidar_feature_extraction_b200 import default_params, synth
+    from oracle import binding as ob
+
+    hp = default_params()
+    sp = synth.spec("vlp16")
+    clouds = [synth.scan_host(sp, f) for f in range(3)]
+    with _fe(hp) as fe:
+        fe.set_stage_timing(mode)
+        for _ in range(3):      # the timed graph is captured once and re-launched
+            out = fe.extract_batch(clouds)
+            ms = np.array(fe.last_stage_ms())
+            assert ms.shape == (6,) and (ms >= 0).all() and ms[1] > 0, ms
+        fe.set_stage_timing(False)
+        plain = fe.extract_batch(clouds)
+    assert np.array_equal(out.labels, plain.labels) and np.array_equal(out.counts, plain.counts)
+    for s, cloud in enumerate(clouds):
+        compare_scan(out, s, cloud, oracle.extract_scan(cloud, oracle_params(ob, hp)), CURV_RTOL)

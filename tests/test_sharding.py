@@ -85,14 +85,16 @@ def _gpu_worker(rank, world, port, out_dir):
     try:
         n_frames = 5
         sp = synth.spec("vlp16")
-        stream = torch.cuda.current_stream(dev)
-        fe = FeatureExtraction(HyperParameters(), device=rank, stream=stream.cuda_stream)
+        # no stream given: the handle creates its own (non-blocking) stream, and the driver must enqueue the
+        # gather on THAT stream (lfx_stream), not on torch's current one
+        fe = FeatureExtraction(HyperParameters(), device=rank)
+        assert fe.stream != 0
         drv = sharding.ShardedExtraction(fe, n_frames, dev)
         clouds = [torch.from_numpy(synth.scan_host(sp, f)).to(dev) for f in range(drv.lo, drv.hi)]
-        for _ in range(3):   # the gather runs on a side stream out of two rotating count buffers
+        for _ in range(3):
             drv.step([fe.wire_view(c) for c in clouds], keep=clouds)
-        drv.join()
-        torch.cuda.synchronize()
+        offs = drv.offsets()   # joins and synchronises the extraction stream
+        assert offs.shape == (n_frames + 1, 2)
         np.save(os.path.join(out_dir, f"gpu_counts_{rank}.npy"), drv.counts_all.cpu().numpy())
         fe.close()
     finally:
