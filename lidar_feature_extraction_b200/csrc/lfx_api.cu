@@ -127,9 +127,15 @@ struct lfx_handle
   double map_prev[12] = {0};
 
   // pinned host staging
+  // descriptor tables: two pinned slots used in turn, so the host can lay out batch k+1 while batch k runs
+  // (h_scans / h_point_base point at the slot of the current batch; desc_done[k] = slot k's H2D copies finished)
+  ScanDesc * h_scans_buf = nullptr;
+  uint64_t * h_point_base_buf = nullptr;
   ScanDesc * h_scans = nullptr;
   uint64_t * h_point_base = nullptr;
   size_t h_scans_cap = 0;
+  cudaEvent_t desc_done[2] = {nullptr, nullptr};
+  int desc_slot = 0;
   uint32_t * h_counters = nullptr;
   // single-scan convenience mirrors
   float4 * h_edge = nullptr, * h_surface = nullptr;
@@ -593,7 +599,8 @@ void lfx_destroy(lfx_handle * h)
   cudaFree(h->d_colored.p); cudaFree(h->d_colored_counts.p);
   cudaFree(h->d_map.p); cudaFree(h->d_map_frames.p);
   for (auto & ev : h->conv_ev) { if (ev) { cudaEventDestroy(ev); } }
-  cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base); cudaFreeHost(h->h_counters);
+  cudaFreeHost(h->h_scans_buf); cudaFreeHost(h->h_point_base_buf); cudaFreeHost(h->h_counters);
+  for (auto & ev : h->desc_done) { if (ev) { cudaEventDestroy(ev); } }
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
   for (auto & ev : h->ev) { if (ev) { cudaEventDestroy(ev); } }
   if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); }
@@ -690,16 +697,24 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
   if (regrown) { drop_graphs(h); }
   if (ns + 1 > h->h_scans_cap) {
     LFX_CUDA(h, cudaStreamSynchronize(h->stream));
-    cudaFreeHost(h->h_scans); cudaFreeHost(h->h_point_base);
+    cudaFreeHost(h->h_scans_buf); cudaFreeHost(h->h_point_base_buf);
+    h->h_scans_buf = nullptr; h->h_point_base_buf = nullptr;
     h->h_scans = nullptr; h->h_point_base = nullptr;
+    h->h_scans_cap = 0;
     const size_t want = ns + ns / 8 + 8;
-    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_scans), want * sizeof(ScanDesc)));
-    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_point_base), (want + 1) * sizeof(uint64_t)));
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_scans_buf), 2 * want * sizeof(ScanDesc)));
+    LFX_CUDA(h, cudaMallocHost(reinterpret_cast<void **>(&h->h_point_base_buf), 2 * (want + 1) * sizeof(uint64_t)));
     h->h_scans_cap = want;
-  } else {
-    // the pinned descriptor table of the previous batch may still be in flight
-    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (auto & ev : h->desc_done) {
+      if (!ev) { LFX_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); }
+    }
   }
+  // the slot written now was last read by the H2D copies of the batch before the previous one: wait for those
+  // only, not for the stream (the previous batch keeps running while this one is laid out and enqueued)
+  h->desc_slot ^= 1;
+  LFX_CUDA(h, cudaEventSynchronize(h->desc_done[h->desc_slot]));
+  h->h_scans = h->h_scans_buf + (size_t)h->desc_slot * h->h_scans_cap;
+  h->h_point_base = h->h_point_base_buf + (size_t)h->desc_slot * (h->h_scans_cap + 1);
 
   // ---- descriptors + H2D of host-resident payloads (adjacent host buffers coalesce into one copy)
   uint64_t pb = 0;
@@ -748,6 +763,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
     LFX_CUDA(h, cudaMemcpyAsync(h->d_scans.p, h->h_scans, sizeof(ScanDesc) * n_scans, cudaMemcpyHostToDevice, h->stream));
   }
   LFX_CUDA(h, cudaMemcpyAsync(h->d_point_base.p, h->h_point_base, sizeof(uint64_t) * (n_scans + 1), cudaMemcpyHostToDevice, h->stream));
+  LFX_CUDA(h, cudaEventRecord(h->desc_done[h->desc_slot], h->stream));
 
   // ---- launch
   h->n_scans = n_scans;
