@@ -329,7 +329,9 @@ def main():
     except Exception:
         uuid = None
     sampler = ClockSampler(local_rank, uuid)
-    sampler.start()
+    no_clocks = os.environ.get("LFX_BENCH_NO_CLOCKS") == "1"    # diagnosis only
+    if not no_clocks:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     e0.record(stream)
@@ -341,7 +343,7 @@ def main():
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if not no_clocks else None
     ms_total = e0.elapsed_time(e1)
     # the events sit on the stream every kernel of the step is launched on, so the host clock around the same
     # region (synchronize included) can only be slightly larger; anything else means the events missed work
@@ -354,6 +356,19 @@ def main():
         ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = n_points * world / (ms_per_step * 1e-3)
+
+    # ---- the exchange alone (N > 1): device time from the end of the batch to the end of the all-gather
+    exchange = None
+    if world > 1 and gather_mode == "sync":
+        sharded.time_gather = True
+        for _ in range(6):
+            step_device()
+        g = sharded.gather_ms()[1:]
+        sharded.time_gather = False
+        t = torch.tensor([float(np.mean(g)), float(np.max(g))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exchange = {"all_gather_ms_mean": float(t[0].item()), "all_gather_ms_max": float(t[1].item()),
+                    "bytes_per_rank": 8 * scans_per_gpu, "how": "CUDA events around the collective on the extraction stream, max over ranks"}
 
     # ---- dominant kernel (k_extract_sectors) timed live with CUDA events on the launching stream
     counts, offsets = np.zeros((scans_per_gpu, 2), np.uint32), np.zeros((scans_per_gpu + 1, 2), np.uint32)
@@ -471,7 +486,7 @@ def main():
                        "sharding": "frames by index, no data-path collective; NCCL all-gather of per-scan counts" if world > 1 else "single GPU",
                        "l2": f"inputs {n_points * 32 / 1e9:.2f} GB per GPU, larger than the 126 MB L2 (no flush needed)",
                        "selected_fraction": n_feat / max(n_points, 1)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "exchange": exchange,
         }
         print(json.dumps(line), flush=True)
     fe.close()

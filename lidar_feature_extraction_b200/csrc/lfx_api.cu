@@ -563,7 +563,10 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
       if ((e = cudaFuncSetAttribute(h->sector_kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sector_smem[c])) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(sectors)"); }
       if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c % N_FAST_K), c >= N_FAST_K) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
       if (occ < 1) { g_create_error = "sector kernel does not fit on this device"; lfx_destroy(h); return LFX_E_CUDA; }
-      h->sector_grid[c] = h->num_sms * occ;
+      // LFX_RESERVE_SMS (experiments): leave that many SMs to kernels of other streams (an overlapped collective)
+      const char * rs = getenv("LFX_RESERVE_SMS");
+      const int reserve = rs ? std::max(0, std::min(atoi(rs), h->num_sms - 1)) : 0;
+      h->sector_grid[c] = (h->num_sms - reserve) * occ;
     }
   }
   const size_t probe_smem = sizeof(uint32_t) * (3 * (size_t)h->opt.max_rings + 1);

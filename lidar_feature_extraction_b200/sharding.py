@@ -105,6 +105,8 @@ class ShardedExtraction:
         self._done = [None, None]
         self._k = 0
         self._main = None
+        self.time_gather = False      # diagnosis: CUDA events around the exchange on the extraction stream
+        self.gather_events = []
 
     def _extraction_stream(self):
         """torch view of the stream the handle launches on: the gather is enqueued THERE (not on whatever torch's
@@ -124,7 +126,19 @@ class ShardedExtraction:
             self.counts_all = cnt
             return res
         with torch.cuda.stream(self._extraction_stream()):
-            return self._step_gather(res, cnt)
+            if not self.time_gather:
+                return self._step_gather(res, cnt)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._step_gather(res, cnt)
+            e1.record()
+            self.gather_events.append((e0, e1))
+            return res
+
+    def gather_ms(self):
+        """Device time per step between the end of the batch and the end of the exchange (time_gather=True)."""
+        self.fe.synchronize()
+        return [a.elapsed_time(b) for a, b in self.gather_events]
 
     def _step_gather(self, res, cnt):
         import torch
