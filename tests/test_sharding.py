@@ -71,7 +71,7 @@ def test_count_all_gather_world_size_2_gloo(tmp_path, n_frames):
     assert off[-1].tolist() == want.sum(axis=0).tolist()
 
 
-def _gpu_worker(rank, world, port, out_dir):
+def _gpu_worker(rank, world, port, out_dir, overlap=False):
     import torch
     import torch.distributed as dist
 
@@ -89,7 +89,7 @@ def _gpu_worker(rank, world, port, out_dir):
         # gather on THAT stream (lfx_stream), not on torch's current one
         fe = FeatureExtraction(HyperParameters(), device=rank)
         assert fe.stream != 0
-        drv = sharding.ShardedExtraction(fe, n_frames, dev)
+        drv = sharding.ShardedExtraction(fe, n_frames, dev, overlap=overlap)
         clouds = [torch.from_numpy(synth.scan_host(sp, f)).to(dev) for f in range(drv.lo, drv.hi)]
         for _ in range(3):
             drv.step([fe.wire_view(c) for c in clouds], keep=clouds)
@@ -102,7 +102,8 @@ def _gpu_worker(rank, world, port, out_dir):
 
 
 @pytest.mark.gpu
-def test_sharded_extraction_two_gpus_nccl(tmp_path, oracle):
+@pytest.mark.parametrize("overlap", [False, True], ids=["gather_on_extraction_stream", "gather_on_side_stream"])
+def test_sharded_extraction_two_gpus_nccl(tmp_path, oracle, overlap):
     import torch
     import torch.multiprocessing as mp
 
@@ -111,7 +112,7 @@ def test_sharded_extraction_two_gpus_nccl(tmp_path, oracle):
     from lidar_feature_extraction_b200 import synth
     from oracle import binding as ob
 
-    mp.spawn(_gpu_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gpu_worker, args=(2, _free_port(), str(tmp_path), overlap), nprocs=2, join=True)
     sp = synth.spec("vlp16")
     want = []
     for f in range(5):
