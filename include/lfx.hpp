@@ -93,6 +93,8 @@ public:
   }
   void Synchronize() { Check(lfx_synchronize(h_)); }
   lfx_handle * handle() { return h_; }
+  // cudaStream_t all work of this handle is enqueued on; chain collectives / timing events on it (lfx_stream).
+  void * stream() const { return lfx_stream(h_); }
 
   // colored_scan of scan `scan` of the last batch (feature_extraction.cpp:153,161): 32-byte pcl::PointXYZRGB records,
   // i.e. PointCloud2.data of the message; needs lfx_options.want_sorted_src (use the two-argument constructor).
