@@ -321,15 +321,17 @@ def main():
     sharded.join()
     torch.cuda.synchronize()
     launches0 = fe.kernel_launches
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    # NVML is initialised (first query included) BEFORE the barrier: it takes milliseconds and a different time on
+    # every rank, and whatever start skew the ranks have after the barrier is paid by all of them at the first exchange
     try:
         uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         uuid = None
     sampler = ClockSampler(local_rank, uuid)
     no_clocks = os.environ.get("LFX_BENCH_NO_CLOCKS") == "1"    # diagnosis only
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     if not no_clocks:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
