@@ -5,7 +5,6 @@
 // (the reference node holds `const HyperParameters params_`, feature_extraction.cpp:173); derived
 // constants (the cosine cut replacing acos(c) < theta) are computed here on the host with the same
 // libm the reference would use.
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -73,9 +72,6 @@ struct lfx_handle
   int sector_grid[2 * N_FAST_K] = {0, 0, 0, 0, 0, 0}, ingest_grid = 0;
   size_t sector_smem[2 * N_FAST_K] = {0, 0, 0, 0, 0, 0};
   bool fast_enabled = false;
-  int regular_src = SRC_TMA;          // staging of regular scans: tensor-map TMA; LFX_SECTOR_SRC=ldg (experiments): 32-byte loads
-  CUtensorMap * d_tmap_tmpl = nullptr; // [N_FAST_K + 1] host-encoded templates (k_probe_layout fills in address / extents / strides)
-  DevBuf<CUtensorMap> d_tmaps;         // [n_scans][2]
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -248,57 +244,23 @@ void (*pick_ring_kernel(int padding, int threads, int * tmax))(const RingArgs)
 }
 
 template<int P, bool DIAG>
-void pick_sector_kernels_t(int regular_src, void (**out)(const SectorArgs))
+void pick_sector_kernels_t(void (**out)(const SectorArgs))
 {
-  if (regular_src == SRC_TMA) {
-    out[0] = k_extract_sectors<P, fast_k(0), DIAG, SRC_TMA>;
-    out[1] = k_extract_sectors<P, fast_k(1), DIAG, SRC_TMA>;
-    out[2] = k_extract_sectors<P, fast_k(2), DIAG, SRC_TMA>;
-  } else {
-    out[0] = k_extract_sectors<P, fast_k(0), DIAG, SRC_LDG>;
-    out[1] = k_extract_sectors<P, fast_k(1), DIAG, SRC_LDG>;
-    out[2] = k_extract_sectors<P, fast_k(2), DIAG, SRC_LDG>;
-  }
-  out[3] = k_extract_sectors<P, fast_k(0), DIAG, SRC_IDX>;
-  out[4] = k_extract_sectors<P, fast_k(1), DIAG, SRC_IDX>;
-  out[5] = k_extract_sectors<P, fast_k(2), DIAG, SRC_IDX>;
+  out[0] = k_extract_sectors<P, fast_k(0), DIAG, false>;
+  out[1] = k_extract_sectors<P, fast_k(1), DIAG, false>;
+  out[2] = k_extract_sectors<P, fast_k(2), DIAG, false>;
+  out[3] = k_extract_sectors<P, fast_k(0), DIAG, true>;
+  out[4] = k_extract_sectors<P, fast_k(1), DIAG, true>;
+  out[5] = k_extract_sectors<P, fast_k(2), DIAG, true>;
 }
 
 // The sector kernel is compiled for the two deployed paddings (compiled default 5, launch YAML 2);
 // any other padding runs on the general ring kernel only.
-bool pick_sector_kernels(int padding, bool diag, int regular_src, void (**out)(const SectorArgs))
+bool pick_sector_kernels(int padding, bool diag, void (**out)(const SectorArgs))
 {
-  if (padding == 5) { if (diag) { pick_sector_kernels_t<5, true>(regular_src, out); } else { pick_sector_kernels_t<5, false>(regular_src, out); } return true; }
-  if (padding == 2) { if (diag) { pick_sector_kernels_t<2, true>(regular_src, out); } else { pick_sector_kernels_t<2, false>(regular_src, out); } return true; }
+  if (padding == 5) { if (diag) { pick_sector_kernels_t<5, true>(out); } else { pick_sector_kernels_t<5, false>(out); } return true; }
+  if (padding == 2) { if (diag) { pick_sector_kernels_t<2, true>(out); } else { pick_sector_kernels_t<2, false>(out); } return true; }
   return false;
-}
-
-// Templates of the per-scan tensor maps (k_probe_layout): rank 3, 32-bit words, box {8 words = one point, 1 ring,
-// `box_firings`}, no swizzle, zeros beyond the edges. The encoder is the driver's (cuTensorMapEncodeTiled), fetched
-// through the runtime so that the library does not link libcuda.
-int encode_tmap_template(CUtensorMap * out, void * any_device_address, int box_firings, std::string & why)
-{
-  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn enc = nullptr;
-  if (!enc) {
-    void * fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
-      why = "cuTensorMapEncodeTiled is not available from this driver";
-      return LFX_E_CUDA;
-    }
-    enc = reinterpret_cast<EncodeFn>(fn);
-  }
-  const cuuint64_t dims[3] = {8, 64, 1024};          // placeholders: replaced per scan on the device
-  const cuuint64_t strides[2] = {32, 64 * 32};
-  const cuuint32_t box[3] = {8, 1, (cuuint32_t)box_firings};
-  const cuuint32_t es[3] = {1, 1, 1};
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, any_device_address, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { why = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return LFX_E_CUDA; }
-  return LFX_OK;
 }
 
 int validate_params(const lfx_params & p, std::string & why)
@@ -331,8 +293,6 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   pa.scan_flags = h->d_scan_flags.p;
   for (int c = 0; c < N_FAST_K; c++) { pa.fast[c] = h->d_fast[c].p; }
   pa.counters = h->d_counters;
-  pa.tmap_tmpl = h->d_tmap_tmpl;
-  pa.tmaps = h->d_tmaps.p;
   pa.max_rings = max_rings;
   pa.P = h->params.padding;
   pa.B = h->params.n_blocks;
@@ -358,7 +318,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       sa.max_rings = max_rings;
       sa.inv_blocks = (uint32_t)(0x100000000ull / (uint64_t)h->params.n_blocks);
       sa.prm = h->dev;
-      h->sector_kernel[c]<<<h->sector_grid[c], sector_warps(fast_k(c), h->regular_src) * 32, h->sector_smem[c], h->stream>>>(sa);
+      h->sector_kernel[c]<<<h->sector_grid[c], sector_warps(fast_k(c), false) * 32, h->sector_smem[c], h->stream>>>(sa);
     }
   }
   if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[2], h->stream, ev_flags)); }
@@ -415,7 +375,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       sa.max_rings = max_rings;
       sa.inv_blocks = (uint32_t)(0x100000000ull / (uint64_t)h->params.n_blocks);
       sa.prm = h->dev;
-      h->sector_kernel[N_FAST_K + c]<<<h->sector_grid[N_FAST_K + c], sector_warps(fast_k(c), SRC_IDX) * 32, h->sector_smem[N_FAST_K + c], h->stream>>>(sa);
+      h->sector_kernel[N_FAST_K + c]<<<h->sector_grid[N_FAST_K + c], sector_warps(fast_k(c), true) * 32, h->sector_smem[N_FAST_K + c], h->stream>>>(sa);
     }
   }
   if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[4], h->stream, ev_flags)); }
@@ -590,33 +550,18 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->pack_grid = h->num_sms * std::max(occ, 1);
   h->ingest_grid = h->num_sms * 8;
   // fast path: compiled for the deployed paddings; the sort-path test knob forces the general kernel
-  {
-    const char * src = getenv("LFX_SECTOR_SRC");
-    h->regular_src = src && strcmp(src, "ldg") == 0 ? SRC_LDG : SRC_TMA;
-  }
   h->fast_enabled = h->opt.force_order_path == 0 && params->n_blocks <= FAST_MAX_BLOCKS &&
-                    pick_sector_kernels(params->padding, h->opt.want_sorted_src || h->opt.want_curvature, h->regular_src, h->sector_kernel);
+                    pick_sector_kernels(params->padding, h->opt.want_sorted_src || h->opt.want_curvature, h->sector_kernel);
   if (h->fast_enabled) {
-    const bool tma = h->regular_src == SRC_TMA;
-    h->sector_smem[0] = tma ? sector_smem_bytes<fast_k(0), SRC_TMA>(sector_warps(fast_k(0), SRC_TMA)) : sector_smem_bytes<fast_k(0), SRC_LDG>(sector_warps(fast_k(0), SRC_LDG));
-    h->sector_smem[1] = tma ? sector_smem_bytes<fast_k(1), SRC_TMA>(sector_warps(fast_k(1), SRC_TMA)) : sector_smem_bytes<fast_k(1), SRC_LDG>(sector_warps(fast_k(1), SRC_LDG));
-    h->sector_smem[2] = tma ? sector_smem_bytes<fast_k(2), SRC_TMA>(sector_warps(fast_k(2), SRC_TMA)) : sector_smem_bytes<fast_k(2), SRC_LDG>(sector_warps(fast_k(2), SRC_LDG));
-    h->sector_smem[3] = sector_smem_bytes<fast_k(0), SRC_IDX>(sector_warps(fast_k(0), SRC_IDX));
-    h->sector_smem[4] = sector_smem_bytes<fast_k(1), SRC_IDX>(sector_warps(fast_k(1), SRC_IDX));
-    h->sector_smem[5] = sector_smem_bytes<fast_k(2), SRC_IDX>(sector_warps(fast_k(2), SRC_IDX));
-    if ((e = cudaMalloc(reinterpret_cast<void **>(&h->d_tmap_tmpl), sizeof(CUtensorMap) * (N_FAST_K + 1))) != cudaSuccess) { return bail(e, "cudaMalloc(tensor map templates)"); }
-    {
-      CUtensorMap tm[N_FAST_K + 1];
-      std::string why;
-      for (int c = 0; c <= N_FAST_K; c++) {
-        if (encode_tmap_template(&tm[c], h->d_tmap_tmpl, c < N_FAST_K ? 16 * fast_k(c) : 32, why) != LFX_OK) { g_create_error = why; lfx_destroy(h); return LFX_E_CUDA; }
-      }
-      if ((e = cudaMemcpy(h->d_tmap_tmpl, tm, sizeof(tm), cudaMemcpyHostToDevice)) != cudaSuccess) { return bail(e, "cudaMemcpy(tensor map templates)"); }
-    }
+    h->sector_smem[0] = sector_smem_bytes<fast_k(0), false>(sector_warps(fast_k(0), false));
+    h->sector_smem[1] = sector_smem_bytes<fast_k(1), false>(sector_warps(fast_k(1), false));
+    h->sector_smem[2] = sector_smem_bytes<fast_k(2), false>(sector_warps(fast_k(2), false));
+    h->sector_smem[3] = sector_smem_bytes<fast_k(0), true>(sector_warps(fast_k(0), true));
+    h->sector_smem[4] = sector_smem_bytes<fast_k(1), true>(sector_warps(fast_k(1), true));
+    h->sector_smem[5] = sector_smem_bytes<fast_k(2), true>(sector_warps(fast_k(2), true));
     for (int c = 0; c < 2 * N_FAST_K; c++) {
-      const int src_c = c >= N_FAST_K ? SRC_IDX : h->regular_src;
       if ((e = cudaFuncSetAttribute(h->sector_kernel[c], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->sector_smem[c])) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(sectors)"); }
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c % N_FAST_K), src_c) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->sector_kernel[c], sector_warps(fast_k(c % N_FAST_K), c >= N_FAST_K) * 32, h->sector_smem[c])) != cudaSuccess) { return bail(e, "occupancy(sectors)"); }
       if (occ < 1) { g_create_error = "sector kernel does not fit on this device"; lfx_destroy(h); return LFX_E_CUDA; }
       // LFX_RESERVE_SMS (experiments): leave that many SMs to kernels of other streams (an overlapped collective)
       const char * rs = getenv("LFX_RESERVE_SMS");
@@ -653,7 +598,6 @@ void lfx_destroy(lfx_handle * h)
   for (int c = 0; c < 2 * N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
   for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_bndx[c].p); }
   cudaFree(h->d_ring_path.p);
-  cudaFree(h->d_tmap_tmpl); cudaFree(h->d_tmaps.p);
   cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p); cudaFree(h->d_conv_tile_cloud.p);
   cudaFree(h->d_colored.p); cudaFree(h->d_colored_counts.p);
   cudaFree(h->d_map.p); cudaFree(h->d_map_frames.p);
@@ -726,7 +670,6 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
   if ((rc = ensure(h, h->d_ring_featoff, ns * mr, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_ring_src, ns * mr, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_scan_flags, ns, &regrown))) { return rc; }
-  if ((rc = ensure(h, h->d_tmaps, 2 * ns, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_gen_scan, ns, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_gen_tile_base, ns + 1, &regrown))) { return rc; }
   if ((rc = ensure(h, h->d_tile_owner, std::max<uint64_t>(total_tiles, 1), &regrown))) { return rc; }
