@@ -164,78 +164,296 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_reference_run(sensor: str, n_scans: int, threads: int, first_frame: int = 0, repeats: int = 1, loops: int = 0):
-    """Time the reference's CPU extraction (oracle/_ref if built, else the C port) on `n_scans` synthetic
-    scans, frames round-robin over `threads` host threads. Returns (points_per_sec, kind, n_points, secs).
-    loops > 0: total time of `loops` passes over the sample instead of the best of `repeats`."""
+PARAMS_NOTE = "compiled defaults (hyper_parameter.hpp:35-43)"
+
+
+def workload_config(workload: str, sensor: str, rings: int, cols: int, scans_per_gpu: int, points_per_gpu: int, world: int) -> dict:
+    """The `config` object of the JSON line: built by this one function for BOTH arms, so that the driver's
+    same-config check compares like with like."""
+    return {"workload": workload, "sensor": sensor, "rings": rings, "cols": cols, "scans_per_gpu": scans_per_gpu,
+            "points_per_gpu": points_per_gpu, "params": PARAMS_NOTE,
+            "sharding": "frames by index, no data-path collective; NCCL all-gather of per-scan counts" if world > 1 else "single GPU",
+            "l2": f"inputs {points_per_gpu * 32 / 1e9:.2f} GB per GPU, larger than the 126 MB L2 (no flush needed)"}
+
+
+def git_blob_sha1(path: str) -> str:
+    """`git hash-object` of a file (what keys profiles/sector_kernel_traffic.json to the kernel source)."""
+    import hashlib
+
+    data = open(path, "rb").read()
+    return hashlib.sha1(b"blob %d\0" % len(data) + data).hexdigest()
+
+
+def cpu_reference_pass(clouds, threads: int):
+    """One pass of the reference's CPU extraction (oracle/_ref if built, else the C port) over `clouds`, scans
+    round-robin over `threads` host threads. Returns (seconds, kind, per-scan results or None for the port)."""
     from concurrent.futures import ThreadPoolExecutor
 
-    from lidar_feature_extraction_b200 import synth
     from oracle import binding as ob
 
-    sp = synth.spec(sensor)
-    clouds = [synth.scan_host(sp, first_frame + f) for f in range(n_scans)]
-    n_points = int(sum(len(c) for c in clouds))
     prm = ob.default_params()
     if ob.Reference.available("stable"):
         ref = ob.Reference("stable")
-        kind = "reference"
-
-        def run_all():
-            with ThreadPoolExecutor(max_workers=threads) as ex:
-                list(ex.map(lambda c: ref.extract_scan(c, prm), clouds))
-    else:
-        orc = ob.Oracle()
-        kind = "port"
-
-        def run_all():
-            orc.extract_batch_counts(clouds, prm, threads)
-    if loops > 0:
-        run_all()   # warm-up pass (page faults, thread pool)
         t0 = time.perf_counter()
-        for _ in range(loops):
-            run_all()
-        dt = time.perf_counter() - t0
-        return n_points * loops / dt, kind, n_points * loops, dt
-    best = None
-    for _ in range(max(repeats, 1)):
-        t0 = time.perf_counter()
-        run_all()
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_points / best, kind, n_points, best
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            results = list(ex.map(lambda c: ref.extract_scan(c, prm), clouds))
+        return time.perf_counter() - t0, "reference", results
+    orc = ob.Oracle()
+    t0 = time.perf_counter()
+    orc.extract_batch_counts(clouds, prm, threads)
+    return time.perf_counter() - t0, "port", None
+
+
+def cpu_reference_run(clouds, threads: int, loops: int = 1):
+    """`loops` timed passes after one warm-up pass (page faults, thread pool). Returns (points_per_sec, kind,
+    points processed, seconds, results of the warm-up pass)."""
+    n_points = int(sum(len(c) for c in clouds))
+    _, kind, results = cpu_reference_pass(clouds, threads)
+    total = 0.0
+    for _ in range(max(loops, 1)):
+        dt, kind, _ = cpu_reference_pass(clouds, threads)
+        total += dt
+    return n_points * max(loops, 1) / total, kind, n_points * max(loops, 1), total, results
+
+
+def parity_check(out, clouds, results, kind: str) -> dict:
+    """The GPU batch `out` (BatchOutput) against the reference's own results on the first len(clouds) scans of the
+    same batch: ring tables, every label byte, per-scan counts, and the edge / surface clouds byte for byte."""
+    from lidar_feature_extraction_b200 import _native as N
+    from lidar_feature_extraction_b200 import synth
+
+    bad_scans, n_pts = 0, 0
+    hist_gpu, hist_ref = np.zeros(256, np.int64), np.zeros(256, np.int64)
+    first_bad = None
+    for s, (cloud, ref) in enumerate(zip(clouds, results)):
+        why = None
+        base = int(out.point_base[s])
+        rings = out.rings[s]
+        kept = [r for r in range(len(rings)) if rings[r]["count"] > 0 and rings[r]["status"] != N.LFX_RING_SPARSE]
+        if kept != [int(r) for r in ref.ring_ids]:
+            why = "ring ids"
+        pos = 0
+        for k, r in enumerate(kept):
+            if why:
+                break
+            cnt, off = int(rings[r]["count"]), int(rings[r]["offset"])
+            if cnt != int(ref.ring_sizes[k]):
+                why = f"ring {r} size"
+                break
+            g, w = out.labels[base + off: base + off + cnt], ref.labels[pos: pos + cnt]
+            hist_gpu += np.bincount(g, minlength=256)
+            hist_ref += np.bincount(w, minlength=256)
+            if not np.array_equal(g, w):
+                why = f"ring {r} labels"
+            pos += cnt
+        n_pts += pos
+        if why is None:
+            x, y, z, _, _ = synth.fields(cloud)
+            src = ref.sorted_src
+            if int(out.counts[s, 0]) != len(ref.edge_idx) or int(out.counts[s, 1]) != len(ref.surface_idx):
+                why = "counts"
+            else:
+                for got, idx, name in ((out.scan_edges(s), ref.edge_idx, "edge"), (out.scan_surfaces(s), ref.surface_idx, "surface")):
+                    want = np.stack([x[src[idx]], y[src[idx]], z[src[idx]], np.ones(len(idx), np.float32)], axis=1)
+                    if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
+                        why = f"{name} cloud"
+        if why is not None:
+            bad_scans += 1
+            first_bad = first_bad or f"scan {s}: {why}"
+    return {"scans": len(clouds), "points": n_pts, "mismatches": bad_scans, "against": kind, "first_mismatch": first_bad,
+            "checked": "ring tables, label bytes, per-scan counts, edge and surface clouds (bitwise), in canonical order",
+            "label_histogram": {str(k): int(v) for k, v in enumerate(hist_gpu[:8])},
+            "label_histogram_equal": bool(np.array_equal(hist_gpu, hist_ref))}
 
 
 def run_reference_arm(args):
+    """The reference's own CPU extraction on the box's host cores; scans come from libsynth.so (host-only), so the
+    CUDA product library is never mapped by this arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sensor, _ = WORKLOADS[args.workload]
+    from lidar_feature_extraction_b200 import synth
+
+    sensor, scans_per_gpu = WORKLOADS[args.workload]
+    if args.scans:
+        scans_per_gpu = args.scans
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sp = synth.spec(sensor)
     cores = host_cores()
-    n_sample = max(2 * cores, 8)
-    if sensor in ("vlp16",):
-        n_sample *= 4
-    for _ in range(args.warmup):
-        cpu_reference_run(sensor, min(n_sample, cores), cores)
-    times, pts = [], 0
+    n_sample = min(max(2 * cores, 8) * (4 if sensor == "vlp16" else 1), scans_per_gpu)
+    if sp.dropout_prob > 0:   # ragged scans: the batch's point count is a property of the data
+        points_per_gpu = int(sum(len(synth.scan_host(sp, f)) for f in range(scans_per_gpu)))
+    else:
+        points_per_gpu = scans_per_gpu * sp.n_rings * sp.n_cols
     kind = "port"
-    for k in range(args.steps):
-        v, kind, n_points, secs = cpu_reference_run(sensor, n_sample, cores, first_frame=k * n_sample)
-        times.append(secs)
-        pts += n_points
-    total = float(sum(times))
+    for _ in range(args.warmup):
+        cpu_reference_pass([synth.scan_host(sp, f) for f in range(min(n_sample, cores))], cores)
+    total, pts = 0.0, 0
+    for k in range(args.steps):   # step k: the k-th block of n_sample frames of rank 0's shard (wrapping around)
+        clouds = [synth.scan_host(sp, (k * n_sample + f) % scans_per_gpu) for f in range(n_sample)]
+        secs, kind, _ = cpu_reference_pass(clouds, cores)
+        total += secs
+        pts += int(sum(len(c) for c in clouds))
     value = pts / total
-    sample = f"{n_sample} synthetic {sensor} scans per step, frames round-robin over {cores} host threads, extraction only"
+    sample = (f"{n_sample} of the workload's {scans_per_gpu} synthetic {sensor} scans per step (consecutive frames of rank 0's shard), "
+              f"scans round-robin over {cores} host threads, extraction only (generation outside the timed region)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "sensor": sensor, "params": "compiled defaults (hyper_parameter.hpp:35-43)"},
+        "config": workload_config(args.workload, sensor, sp.n_rings, sp.n_cols, scans_per_gpu, points_per_gpu, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+STAGES = ("probe", "sectors", "bucketing", "sectors_indexed", "rings", "pack")
+
+
+def make_inputs(fe, lib, sp, first_frame: int, scans: int, dev):
+    """`scans` synthetic scans resident in HBM: generated on the device, or on the host when the sensor has drop-outs
+    (ragged scans). Returns (uint8 tensor [points, 32], per-scan sizes, host clouds or None)."""
+    import torch
+
+    from lidar_feature_extraction_b200 import synth
+
+    per_scan = sp.n_rings * sp.n_cols
+    if sp.dropout_prob > 0:
+        clouds = [synth.scan_host(sp, first_frame + f) for f in range(scans)]
+        sizes = [len(c) for c in clouds]
+        return torch.from_numpy(np.concatenate(clouds, axis=0)).to(dev), sizes, clouds
+    d_in = torch.empty((scans * per_scan, 32), dtype=torch.uint8, device=dev)
+    rc = lib.lfx_synth_batch_device(fe.handle, C.byref(sp), first_frame, scans, d_in.data_ptr())
+    assert rc == 0, rc
+    return d_in, [per_scan] * scans, None
+
+
+def stage_times(fe, views, keep, mode: int, sync: bool, iters: int):
+    fe.set_stage_timing(mode)
+    rows = []
+    for _ in range(iters + 1):
+        fe.extract_views(views, keep=keep)
+        if sync:
+            fe.synchronize()
+        rows.append(fe.last_stage_ms())
+    fe.set_stage_timing(False)
+    return np.array(rows[1:])
+
+
+def measure_workload(name: str, local_rank: int, dev, stream, steps: int, peak: float) -> dict:
+    """One of the other BASELINE.json configs, device-resident, single GPU: same timing rules as the headline (CUDA
+    events on the launching stream, >= 3 warm-up steps, inputs larger than L2), fewer extras."""
+    import torch
+
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, synth
+    from lidar_feature_extraction_b200 import _native as N
+
+    sensor, scans = WORKLOADS[name]
+    sp = synth.spec(sensor)
+    lib = N.lib()
+    fe = FeatureExtraction(HyperParameters(), device=local_rank, stream=stream.cuda_stream, max_rings=max(128, sp.n_rings))
+    d_in, sizes, _ = make_inputs(fe, lib, sp, 0, scans, dev)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n_points = int(offs[-1])
+    views = FeatureExtraction.view_array(
+        [FeatureExtraction.wire_view((d_in.data_ptr() + int(offs[s]) * 32, sizes[s])) for s in range(scans)])
+    for _ in range(3):
+        fe.extract_views(views, keep=d_in)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fe.extract_views(views, keep=d_in)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    counts, offsets = np.zeros((scans, 2), np.uint32), np.zeros((scans + 1, 2), np.uint32)
+    lib.lfx_fetch_counts(fe.handle, counts.ctypes.data, offsets.ctypes.data)
+    n_feat = int(offsets[-1, 0]) + int(offsets[-1, 1])
+    alg = 32 * n_points + n_points + 16 * n_feat + 8 * scans
+    stage = stage_times(fe, views, d_in, 2, False, 3)
+    kernel_ms = float((stage[:, 1] + stage[:, 3]).mean())
+    out = {"ms_per_step": ms, "value": n_points / (ms * 1e-3), "unit": UNIT, "steps": steps, "points_per_step": n_points,
+           "scans": scans, "input_gb": n_points * 32 / 1e9, "algorithmic_bytes": alg,
+           "pipeline_frac": alg / (ms * 1e-3) / 1e9 / peak, "kernel_frac": alg / (kernel_ms * 1e-3) / 1e9 / peak,
+           "stage_ms": {k: float(stage[:, i].mean()) for i, k in enumerate(STAGES)}, "paths": fe.batch_stats(),
+           "selected_fraction": n_feat / max(n_points, 1)}
+    fe.close()
+    del d_in
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_chain(local_rank: int, dev, stream, steps: int, peak: float, scans: int = 1250) -> dict:
+    """/points_raw -> k_convert -> extraction without leaving the device: Ouster-like 48-byte driver clouds (3 % of the
+    returns zeroed, so the converted clouds are ragged and take the bucketing + indexed sector path)."""
+    import torch
+
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, PointCloud2, PointField, PointTypeConverter, synth
+    from lidar_feature_extraction_b200 import _native as N
+
+    sp = synth.spec("os128")
+    per = sp.n_rings * sp.n_cols
+    lib = N.lib()
+    fe = FeatureExtraction(HyperParameters(), device=local_rank, stream=stream.cuda_stream, max_rings=128)
+    wire, _, _ = make_inputs(fe, lib, sp, 0, scans, dev)
+    torch.cuda.synchronize()
+    # Ouster driver layout (test_convert.py:177-187): x,y,z f32 @0, intensity f32 @16, t u32 @20, reflectivity u16 @24,
+    # ring u8 @26, noise u16 @28, range u32 @32, point_step 48
+    raw = torch.zeros((scans * per, 48), dtype=torch.uint8, device=dev)
+    raw[:, 0:12] = wire[:, 0:12]
+    raw[:, 16:20] = wire[:, 16:20]
+    raw[:, 26] = wire[:, 20]
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xC0FFEE)
+    dead = torch.rand(scans * per, device=dev, generator=g) < 0.03
+    raw[dead] = 0
+    del wire, dead
+    fields = [PointField("x", 0, 7), PointField("y", 4, 7), PointField("z", 8, 7), PointField("intensity", 16, 7), PointField("t", 20, 6),
+              PointField("reflectivity", 24, 4), PointField("ring", 26, 2), PointField("noise", 28, 4), PointField("range", 32, 6)]
+    raw3 = raw.view(scans, per, 48)
+    msgs = [PointCloud2(data=raw3[s], point_step=48, fields=fields) for s in range(scans)]
+    conv = PointTypeConverter(fe)
+
+    def chain_step():
+        conv.convert_batch(msgs)
+        fe.extract_views(fe.view_array([conv.view(s) for s in range(scans)]))
+
+    for _ in range(3):
+        chain_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(steps):
+        chain_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3 / steps
+    ms = max(e0.elapsed_time(e1) / steps, wall)   # the converter's call is synchronous (it returns the kept counts)
+    cms = C.c_float()
+    lib.lfx_last_convert_ms(fe.handle, C.byref(cms))
+    kept = sum(int(conv.kept(s)) for s in range(scans))
+    counts, offsets = np.zeros((scans, 2), np.uint32), np.zeros((scans + 1, 2), np.uint32)
+    lib.lfx_fetch_counts(fe.handle, counts.ctypes.data, offsets.ctypes.data)
+    n_feat = int(offsets[-1, 0]) + int(offsets[-1, 1])
+    n = scans * per
+    alg = 48 * n + 32 * kept + 32 * kept + kept + 16 * n_feat + 8 * scans   # converter (raw in, 32 B out) + extraction
+    fe.set_stage_timing(True)
+    chain_step()
+    fe.synchronize()
+    st = fe.last_stage_ms()
+    fe.set_stage_timing(False)
+    out = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "raw points/s", "steps": steps, "points_per_step": n, "scans": scans,
+           "kept_fraction": kept / n, "algorithmic_bytes": alg, "pipeline_frac": alg / (ms * 1e-3) / 1e9 / peak,
+           "convert_kernel_ms": float(cms.value), "stage_ms": {k: float(st[i]) for i, k in enumerate(STAGES)}, "paths": fe.batch_stats()}
+    conv.close()
+    fe.close()
+    del raw, raw3, msgs
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -248,6 +466,7 @@ def main():
     ap.add_argument("--scans", type=int, default=0, help="override scans per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the other BASELINE.json configs and the converter chain")
     ap.add_argument("--e2e-steps", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -292,15 +511,7 @@ def main():
     lib = N.lib()
 
     # ---- inputs resident in HBM (generated on device; host-generated when the sensor has drop-outs)
-    if sp.dropout_prob > 0:
-        clouds = [synth.scan_host(sp, first_frame + f) for f in range(scans_per_gpu)]
-        sizes = [len(c) for c in clouds]
-        d_in = torch.from_numpy(np.concatenate(clouds, axis=0)).to(dev)
-    else:
-        sizes = [per_scan] * scans_per_gpu
-        d_in = torch.empty((scans_per_gpu * per_scan, 32), dtype=torch.uint8, device=dev)
-        rc = lib.lfx_synth_batch_device(fe.handle, C.byref(sp), first_frame, scans_per_gpu, d_in.data_ptr())
-        assert rc == 0, rc
+    d_in, sizes, _ = make_inputs(fe, lib, sp, first_frame, scans_per_gpu, dev)
     torch.cuda.synchronize()
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n_points = int(offs[-1])
@@ -379,41 +590,36 @@ def main():
     alg_bytes = 32 * n_points + n_points + 16 * n_feat + 8 * scans_per_gpu  # SURVEY.md 8(d) / BASELINE.md 4
     # (a) as in the timed region: the batch runs as its CUDA graph, steps back to back, the stage events are
     #     event-record nodes of that graph; (b) eager launches with a synchronize between steps, for comparison
-    def stage_loop(mode, sync):
-        fe.set_stage_timing(mode)
-        rows = []
-        for _ in range(max(3, min(args.steps, 10)) + 1):
-            fe.extract_views(dev_views, keep=d_in)
-            if sync:
-                fe.synchronize()
-            rows.append(fe.last_stage_ms())
-        fe.set_stage_timing(False)
-        return np.array(rows[1:])
-    stage = stage_loop(2, False)
-    stage_eager = stage_loop(1, True)
+    stage = stage_times(fe, dev_views, d_in, 2, False, max(3, min(args.steps, 10)))
+    stage_eager = stage_times(fe, dev_views, d_in, 1, True, max(3, min(args.steps, 10)))
     # k_extract_sectors: launches on regular scans (stage 1) + launches on bucketed rings (stage 3); on a given
     # workload one instantiation holds (nearly) the whole batch
     ring_ms = float((stage[:, 1] + stage[:, 3]).mean())
     peaks, peak_kind = measured_peaks()
     peak = float(peaks["hbm_gbs"])
     achieved = alg_bytes / (ring_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, "no ncu capture of this kernel source / sensor under profiles/"
     try:
-        # dram__bytes_read + dram__bytes_write of one launch of the sector kernel (ncu --set full), per point
+        # dram__bytes_read + dram__bytes_write of one launch of the sector kernel (ncu --set full), per point. It cannot
+        # be measured inside this run (it needs the profiler), so the committed figure is keyed to the git blob of the
+        # kernel source it was captured from and is reported only while that source is unchanged
         with open(os.path.join(ROOT, "profiles", "sector_kernel_traffic.json")) as f:
             tj = json.load(f)
-        traffic = float(tj["dram_bytes_per_point"][sensor]) * n_points
+        blob = git_blob_sha1(os.path.join(ROOT, "lidar_feature_extraction_b200", "csrc", "lfx_sector.cuh"))
+        if tj.get("sector_cuh_blob") == blob and sensor in tj["dram_bytes_per_point"]:
+            traffic = float(tj["dram_bytes_per_point"][sensor]) * n_points
+            traffic_note = f"ncu capture {tj.get('capture', '?')} of lfx_sector.cuh blob {blob[:12]}"
+        elif tj.get("sector_cuh_blob") != blob:
+            traffic_note = f"lfx_sector.cuh (blob {blob[:12]}) changed since the capture (blob {str(tj.get('sector_cuh_blob'))[:12]})"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "k_extract_sectors", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_kind": f"of {peak_kind}",
                 "kernel_ms": ring_ms, "algorithmic_bytes": alg_bytes,
-                "stage_ms": {"probe": float(stage[:, 0].mean()), "sectors": float(stage[:, 1].mean()),
-                             "bucketing": float(stage[:, 2].mean()), "sectors_indexed": float(stage[:, 3].mean()),
-                             "rings": float(stage[:, 4].mean()), "pack": float(stage[:, 5].mean())},
+                "stage_ms": {k: float(stage[:, i].mean()) for i, k in enumerate(STAGES)},
                 "stage_ms_how": "event-record nodes inside the batch's CUDA graph, steps back to back as in the timed region",
                 "kernel_ms_eager": float((stage_eager[:, 1] + stage_eager[:, 3]).mean()),
-                "paths": fe.batch_stats(),
+                "paths": fe.batch_stats(), "selected_fraction": n_feat / max(n_points, 1),
                 "pipeline_frac": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
 
     # ---- e2e: same metric through the public C ABI with pinned HOST buffers
@@ -467,28 +673,44 @@ def main():
         lib.lfx_host_free(h_edge)
         lib.lfx_host_free(h_surf)
 
-    # ---- CPU baseline on the box's host cores (rank 0, N=1 only; bounded sample)
-    cpu = None
+    # ---- CPU baseline on the box's host cores (rank 0, N=1 only; bounded sample) and, with its results, parity of
+    #      THIS run's GPU batch: the reference extracts the first n_sample scans of the very buffer the GPU timed
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         # bounded sample: ~10 s of CPU work (the reference runs ~2 Mpts/s per thread)
-        n_sample = max(int(4.0e6 * cores / per_scan), cores)
+        n_sample = min(max(int(4.0e6 * cores / per_scan), cores), scans_per_gpu)
         loops = 5
-        v, kind, pts, secs = cpu_reference_run(sensor, n_sample, cores, loops=loops)
+        sample = d_in[: int(offs[n_sample])].cpu().numpy()
+        clouds = [sample[int(offs[s]): int(offs[s + 1])] for s in range(n_sample)]
+        v, kind, pts, secs, results = cpu_reference_run(clouds, cores, loops=loops)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"{n_sample} synthetic {sensor} scans x {loops} passes ({pts} points, {secs:.2f} s), frames round-robin over {cores} host threads, extraction only"}
+               "sample": f"the first {n_sample} scans of the timed batch x {loops} passes ({pts} points, {secs:.2f} s), scans round-robin over {cores} host threads, extraction only"}
+        if results is not None:
+            fe.extract_views(dev_views, keep=d_in)
+            parity = parity_check(fe.fetch(fetch_points=True), clouds, results, kind)
+        del sample, clouds
+
+    # ---- the other BASELINE.json configs and the deployed chain, a few steps each (rank 0, N=1 only)
+    workloads = None
+    if rank == 0 and world == 1 and not args.no_workloads:
+        fe.close()
+        del d_in
+        torch.cuda.empty_cache()
+        workloads = {}
+        for name in sorted(WORKLOADS):
+            if name != args.workload:
+                workloads[name] = measure_workload(name, local_rank, dev, stream, max(5, min(args.steps, 10)), peak)
+        workloads["os128_raw_convert_extract"] = measure_chain(local_rank, dev, stream, max(3, min(args.steps, 5)), peak)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": args.workload, "sensor": sensor, "rings": sp.n_rings, "cols": sp.n_cols,
-                       "scans_per_gpu": scans_per_gpu, "points_per_gpu": n_points, "params": "compiled defaults (hyper_parameter.hpp:35-43)",
-                       "sharding": "frames by index, no data-path collective; NCCL all-gather of per-scan counts" if world > 1 else "single GPU",
-                       "l2": f"inputs {n_points * 32 / 1e9:.2f} GB per GPU, larger than the 126 MB L2 (no flush needed)",
-                       "selected_fraction": n_feat / max(n_points, 1)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "exchange": exchange,
+            "config": workload_config(args.workload, sensor, sp.n_rings, sp.n_cols, scans_per_gpu, n_points, world),
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "exchange": exchange, "workloads": workloads,
         }
         print(json.dumps(line), flush=True)
     fe.close()

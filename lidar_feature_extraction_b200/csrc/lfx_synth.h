@@ -175,5 +175,45 @@ LFX_HD float start_azimuth(const lfx_synth_spec & s, uint64_t frame)
   return 6.28318530717958647692f * u01(draw(s.seed, frame, 0xFFFFu, 0xFFFFFFu, 5));
 }
 
+// ---- the host entry points (lfx_synth_named / lfx_synth_scan_host), shared by liblfx.so and by libsynth.so: the
+//      second one is a host-only library, so that a process that only needs scans (bench.py's reference arm, the
+//      oracle tests) does not have to map the CUDA product library
+inline int named(const char * name, lfx_synth_spec * out)
+{
+  if (!name || !out) { return LFX_E_BAD_PARAM; }
+  lfx_synth_spec s{};
+  s.range_noise = 0.005f;
+  s.dropout_prob = 0.0f;
+  s.dropout_burst = 16.0f;
+  s.near_prob = 0.0f;
+  s.world = LFX_WORLD_ROOM;
+  auto is = [&](const char * n) { const char * a = name; while (*a && *a == *n) { a++; n++; } return *a == 0 && *n == 0; };
+  if (is("vlp16")) { s.n_rings = 16; s.n_cols = 1800; s.elev_lo_deg = -15.0f; s.elev_hi_deg = 15.0f; s.seed = 0xC0FFEEull ^ 1; }
+  else if (is("hdl32")) { s.n_rings = 32; s.n_cols = 2170; s.elev_lo_deg = -30.67f; s.elev_hi_deg = 10.67f; s.seed = 0xC0FFEEull ^ 2; }
+  else if (is("hdl64")) {
+    s.n_rings = 64; s.n_cols = 2048; s.elev_lo_deg = 2.0f; s.elev_hi_deg = -24.8f; s.seed = 0xC0FFEEull ^ 3;
+    s.world = LFX_WORLD_TUNNEL; s.dropout_prob = 0.01f; s.near_prob = 0.0005f;
+  }
+  else if (is("os128")) { s.n_rings = 128; s.n_cols = 2048; s.elev_lo_deg = -22.5f; s.elev_hi_deg = 22.5f; s.seed = 0xC0FFEEull ^ 4; }
+  else { return LFX_E_BAD_PARAM; }
+  *out = s;
+  return LFX_OK;
+}
+
+inline int scan_host(const lfx_synth_spec * spec, uint64_t frame, void * out, uint32_t * n_points_out)
+{
+  if (!spec || !out || !n_points_out || spec->n_rings <= 0 || spec->n_cols <= 0 || spec->n_rings > 65535) { return LFX_E_BAD_PARAM; }
+  Point32 * p = static_cast<Point32 *>(out);
+  const float az0 = start_azimuth(*spec, frame);
+  uint32_t n = 0;
+  for (int col = 0; col < spec->n_cols; col++) {
+    for (int ring = 0; ring < spec->n_rings; ring++) {
+      if (make_point(*spec, frame, az0, (uint32_t)ring, (uint32_t)col, &p[n])) { n++; }
+    }
+  }
+  *n_points_out = n;
+  return LFX_OK;
+}
+
 }  // namespace lfx_synth
 #endif  // LFX_SYNTH_H_

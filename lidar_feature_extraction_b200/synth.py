@@ -1,18 +1,37 @@
-"""Synthetic scans for the BASELINE.json sensor shapes (bindings of lfx_synth_* in include/lfx.h)."""
+"""Synthetic scans for the BASELINE.json sensor shapes (bindings of lfx_synth_* in include/lfx.h).
+
+The host generator is loaded from ``libsynth.so``, a host-only build of the same code (csrc/lfx_synth_host.cpp), so that
+generating scans does not map the CUDA product library: bench.py's reference arm and the oracle-only tests run
+without ``liblfx.so`` in their address space. The device generator (``lfx_synth_batch_device``) lives in ``liblfx.so``."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import _native as N
 
 NAMES = ("vlp16", "hdl32", "hdl64", "os128")
+SYNTH_LIB_PATH = os.path.join(N.PKG_DIR, "libsynth.so")
+_synth = None
+
+
+def _lib() -> C.CDLL:
+    global _synth
+    if _synth is None:
+        if not os.path.exists(SYNTH_LIB_PATH):
+            raise ImportError(f"{SYNTH_LIB_PATH} is missing (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+        L = C.CDLL(SYNTH_LIB_PATH)
+        L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(N.SynthSpec)]
+        L.lfx_synth_scan_host.argtypes = [C.POINTER(N.SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
+        _synth = L
+    return _synth
 
 
 def spec(name: str, **overrides) -> N.SynthSpec:
     s = N.SynthSpec()
-    if N.lib().lfx_synth_named(name.encode(), C.byref(s)) != N.LFX_OK:
+    if _lib().lfx_synth_named(name.encode(), C.byref(s)) != N.LFX_OK:
         raise ValueError(f"unknown synthetic sensor {name!r}; known: {NAMES}")
     for k, v in overrides.items():
         setattr(s, k, v)
@@ -23,7 +42,7 @@ def scan_host(sp: N.SynthSpec, frame: int) -> np.ndarray:
     """One scan as PointCloud2 payload bytes: uint8 array [n_points, 32] (deployed wire layout)."""
     buf = np.zeros((sp.n_rings * sp.n_cols, 32), dtype=np.uint8)
     n = C.c_uint32(0)
-    rc = N.lib().lfx_synth_scan_host(C.byref(sp), frame, buf.ctypes.data, C.byref(n))
+    rc = _lib().lfx_synth_scan_host(C.byref(sp), frame, buf.ctypes.data, C.byref(n))
     if rc != N.LFX_OK:
         raise RuntimeError(f"lfx_synth_scan_host failed: {rc}")
     return buf[: n.value]
