@@ -135,7 +135,23 @@ typedef struct lfx_ring_info {
  * Within a scan: rings ascending by id, inside a ring ascending sorted index
  * (GetIndicesByValue, lib/include/lidar_feature_library/algorithm.hpp:50-62). Scans concatenated
  * in batch order; scan s owns [offsets[2s], offsets[2s]+counts[2s]) of edge_xyz and
- * [offsets[2s+1], ...+counts[2s+1]) of surface_xyz. */
+ * [offsets[2s+1], ...+counts[2s+1]) of surface_xyz.
+ *
+ * Where this differs from the reference AS SHIPPED (consumers of the topics, read this):
+ *  - ORDER of the points inside scan_edge / scan_surface / colored_scan. The reference appends ring after ring in the
+ *    iteration order of a std::unordered_map (feature_extraction.cpp:120), i.e. in an unspecified order; here rings
+ *    are ascending by id. The per-ring content (the SET of points with each label) is the same
+ *    (tests/test_oracle_vs_ref.py::test_feature_sets_match_the_verbatim_reference_independent_of_order);
+ *    localization and mapping build kd-trees / concatenate these clouds and do not depend on the order.
+ *  - TIES. Argsort (algorithm.hpp:65-71) and SortByAtan2 (ring.hpp:101-112) use std::sort, which leaves the order of
+ *    equal keys to the library. Here equal curvatures are walked in index order and equal polar angles keep source
+ *    order, i.e. the results are those of the reference built with a stable (value, index) sort
+ *    (oracle/_ref/libref_stable.so: the bit-exact parity bar). Exact curvature ties do not occur on float32 sensor
+ *    data; on constructed inputs that have them, the shipped reference's own labels depend on its libstdc++.
+ *
+ * Host buffers behind LFX_MEM_HOST views: lfx_extract_batch returns before their host-to-device copies have
+ * finished. They must stay valid and unmodified until the NEXT-BUT-ONE lfx_extract_batch on the handle has returned
+ * (two descriptor slots), or until lfx_synchronize / any lfx_fetch_* of this batch has returned. */
 typedef struct lfx_batch_result {
   int n_scans;
   uint64_t total_points;

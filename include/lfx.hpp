@@ -38,9 +38,14 @@ struct PointField { std::string name; uint32_t offset; uint8_t datatype; };
 
 // Field lookup by name, as pcl::fromROSMsg does for PointXYZIR (lib/include/lidar_feature_library/point_type.hpp:83-86).
 // RingIsAvailable (ring.cpp:36-44) becomes view.has_ring; is_dense is taken from the message.
+// data_bytes: size of the message's data array (msg->data.size()); when given, a message whose width * height *
+// point_step exceeds it is refused here instead of becoming an out-of-bounds read of the copy engine.
 inline lfx_cloud_view MakeView(const void * data, uint32_t n_points, uint32_t point_step, const std::vector<PointField> & fields,
-                               bool is_dense, bool device_memory = false)
+                               bool is_dense, bool device_memory = false, size_t data_bytes = 0)
 {
+  if (data_bytes != 0 && static_cast<uint64_t>(n_points) * point_step > data_bytes) {
+    throw Error(LFX_E_BAD_LAYOUT, "width * height * point_step exceeds the size of the data array");
+  }
   lfx_cloud_view v;
   std::memset(&v, 0, sizeof(v));
   v.data = data;
@@ -92,6 +97,16 @@ public:
     return res;
   }
   void Synchronize() { Check(lfx_synchronize(h_)); }
+  // Ring ids of scan 0 of the last call that contributed nothing because the reference's per-ring code throws for
+  // them (feature_extraction.cpp:154-156 logs a warning per such ring): lfx_ring_info.status == LFX_RING_SKIPPED.
+  std::vector<int> SkippedRings(int max_rings = 128)
+  {
+    std::vector<lfx_ring_info> rings(static_cast<size_t>(max_rings));
+    Check(lfx_fetch_rings(h_, rings.data()));
+    std::vector<int> ids;
+    for (int r = 0; r < max_rings; r++) { if (rings[r].status == LFX_RING_SKIPPED) { ids.push_back(r); } }
+    return ids;
+  }
   lfx_handle * handle() { return h_; }
   // cudaStream_t all work of this handle is enqueued on; chain collectives / timing events on it (lfx_stream).
   void * stream() const { return lfx_stream(h_); }

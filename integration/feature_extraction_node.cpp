@@ -98,7 +98,7 @@ private:
     for (const auto & f : msg->fields) { fields.push_back({f.name, f.offset, f.datatype}); }
     lfx_scan_output out;
     try {
-      const lfx_cloud_view view = lfx::MakeView(msg->data.data(), msg->width * msg->height, msg->point_step, fields, msg->is_dense);
+      const lfx_cloud_view view = lfx::MakeView(msg->data.data(), msg->width * msg->height, msg->point_step, fields, msg->is_dense, false, msg->data.size());
       out = fe_.Extract(view);   // replaces feature_extraction.cpp:110-157
     } catch (const lfx::Error & e) {
       // LFX_E_NOT_DENSE / LFX_E_NO_RING: feature_extraction.cpp:96-108 logs and shuts down
@@ -106,16 +106,20 @@ private:
       rclcpp::shutdown();
       return;
     }
+    // feature_extraction.cpp:154-156: one warning per ring whose per-ring code throws in the reference (too few points
+    // for the convolution / the sectors, two adjacent points on the sensor axis); such a ring contributes nothing
+    for (const int ring : fe_.SkippedRings()) {
+      RCLCPP_WARN(get_logger(), "ring %d was skipped (the reference throws std::invalid_argument for it)", ring);
+    }
     std_msgs::msg::Header header = msg->header;       // stamp = input stamp (consumers sync on it, subscriber.hpp:72-75)
     header.frame_id = "lidar_feature_base_link";      // feature_extraction.cpp:159
     edge_pub_->publish(MakeXYZCloud(out.edge_xyz, out.n_edge, header));           // :163-170
     surface_pub_->publish(MakeXYZCloud(out.surface_xyz, out.n_surface, header));
     // colored_scan (depth-1 debug topic, :77-78,153,161,168): built on the device when the handle was created with
     // lfx_options.want_sorted_src; the bytes are PointCloud2.data of the pcl::PointXYZRGB message
-    if (colored_pub_->get_subscription_count() > 0) {
-      const std::vector<uint8_t> colored = fe_.ColoredScan();
-      colored_pub_->publish(MakeCloud(LFX_TOPIC_COLORED_SCAN, colored.data(), static_cast<uint32_t>(colored.size() / 32), header));
-    }
+    // (published on every callback like the reference does, :168, whether or not anybody listens)
+    const std::vector<uint8_t> colored = fe_.ColoredScan();
+    colored_pub_->publish(MakeCloud(LFX_TOPIC_COLORED_SCAN, colored.data(), static_cast<uint32_t>(colored.size() / 32), header));
   }
 
   lfx::FeatureExtraction fe_;

@@ -642,8 +642,9 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
     }
     const uint32_t ring_bytes = v.ring_datatype == LFX_RING_U8 ? 1 : (v.ring_datatype == LFX_RING_U16 ? 2 : 4);
     if (v.n_points > 0 && !v.data) { return fail(h, LFX_E_BAD_LAYOUT, "null data with n_points > 0"); }
-    if (v.point_step < 12 || v.off_x + 4 > v.point_step || v.off_y + 4 > v.point_step || v.off_z + 4 > v.point_step ||
-        v.off_ring + ring_bytes > v.point_step) {
+    // (64-bit sums: offsets near 2^32 must not wrap past the check)
+    if (v.point_step < 12 || (uint64_t)v.off_x + 4 > v.point_step || (uint64_t)v.off_y + 4 > v.point_step ||
+        (uint64_t)v.off_z + 4 > v.point_step || (uint64_t)v.off_ring + ring_bytes > v.point_step) {
       return fail(h, LFX_E_BAD_LAYOUT, "field offsets exceed point_step");
     }
     if ((v.point_step | v.off_x | v.off_y | v.off_z) % 4 != 0 || v.off_ring % ring_bytes != 0 ||
@@ -1521,30 +1522,37 @@ int lfx_map_add_batch(lfx_handle * h, const lfx_pose * poses, int n_poses, uint8
     LFX_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   // MapBuilder::Callback, map.hpp:104-127, frame by frame (translation_threshold 1.0, rotation_threshold 0.1, :92-93)
+  // The gate runs on copies of its state: the handle only advances once the frames it selected are in the map (a
+  // failed reservation or launch must not leave later frames gated against a pose whose frame was never added).
   std::vector<MapFrame> frames;
   uint64_t dst = h->map_points;
   uint32_t longest = 0;
+  bool gate_empty = h->map_empty;
+  double gate_prev[12];
+  memcpy(gate_prev, h->map_prev, sizeof(gate_prev));
   for (int s = 0; s < ns; s++) {
     if (selected_out) { selected_out[s] = 0; }
     const uint32_t n = offsets[2 * ((size_t)s + 1)] - offsets[2 * (size_t)s];
     if (n == 0) { continue; }                                                       // :117-120
     double m[12];
     pose_matrix(poses[s], m);
-    if (!h->map_empty && pose_diff_small(h->map_prev, m, 1.0, 0.1)) { continue; }   // :122-128
+    if (!gate_empty && pose_diff_small(gate_prev, m, 1.0, 0.1)) { continue; }       // :122-128
     MapFrame f;
     memcpy(f.m, m, sizeof(m));
     f.dst = dst; f.src = offsets[2 * (size_t)s]; f.n = n;
     frames.push_back(f);
     dst += n;
     longest = std::max(longest, n);
-    memcpy(h->map_prev, m, sizeof(m));                                              // :131
-    h->map_empty = false;
+    memcpy(gate_prev, m, sizeof(m));                                                // :131
+    gate_empty = false;
     if (selected_out) { selected_out[s] = 1; }
   }
   if (!frames.empty()) {
     int rc;
-    if ((rc = map_reserve(h, dst))) { return rc; }
-    if ((rc = ensure(h, h->d_map_frames, frames.size(), nullptr))) { return rc; }
+    if ((rc = map_reserve(h, dst)) || (rc = ensure(h, h->d_map_frames, frames.size(), nullptr))) {
+      if (selected_out) { memset(selected_out, 0, (size_t)ns); }   // nothing was added
+      return rc;
+    }
     LFX_CUDA(h, cudaMemcpyAsync(h->d_map_frames.p, frames.data(), sizeof(MapFrame) * frames.size(), cudaMemcpyHostToDevice, h->stream));
     const unsigned gy = (unsigned)std::min<uint32_t>(std::max<uint32_t>((longest + MAP_THREADS * 4 - 1) / (MAP_THREADS * 4), 1u), 64u);
     for (size_t f0 = 0; f0 < frames.size(); f0 += 1u << 30) {
@@ -1555,6 +1563,8 @@ int lfx_map_add_batch(lfx_handle * h, const lfx_pose * poses, int n_poses, uint8
     }
     LFX_CUDA(h, cudaStreamSynchronize(h->stream));   // `frames` is host memory of this call
     h->map_points = dst;
+    h->map_empty = gate_empty;
+    memcpy(h->map_prev, gate_prev, sizeof(gate_prev));
   }
   if (map_points_out) { *map_points_out = h->map_points; }
   return LFX_OK;

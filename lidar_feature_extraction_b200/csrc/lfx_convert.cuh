@@ -18,6 +18,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef LFX_CONVERT_TICKET
+#define LFX_CONVERT_TICKET 1
+#endif
+
 namespace lfxk
 {
 
@@ -183,11 +187,20 @@ k_convert(const ConvArgs a)
   if (tid == 0) { conv_mbar_init(&s_bar[0]); }
   uint32_t phase[1] = {0u};
 
-  // start staging this CTA's tile into buffer b. Tile = blockIdx.x: CTAs of a 1-D grid are dispatched in index
-  // order, so every earlier tile has started (the same assumption CUB's decoupled look-back scan makes).
+  // start staging this CTA's tile into buffer b. The tile comes from an atomic ticket, so a tile's predecessors in the
+  // look-back chain have started by construction, whatever order the hardware dispatches CTAs in (blockIdx order is
+  // what happens in practice but is not guaranteed: MPS, time slicing, a debugger). -DLFX_CONVERT_TICKET=0 takes
+  // tile = blockIdx.x instead (3 % faster on the os128 bench, profiles/r01_summary.md) and relies on in-order dispatch.
   auto fetch = [&](int b) {
+#if LFX_CONVERT_TICKET
+    if (tid == 0) { s_tile[b] = atomicAdd(a.ticket, 1u); }
+    __syncthreads();
+    const uint32_t tile = s_tile[b];
+    if (tile >= a.n_tiles) { return; }
+#else
     const uint32_t tile = blockIdx.x;
     if (tid == 0) { s_tile[b] = tile; }
+#endif
     const int c = (int)a.tile_cloud[tile];
     if (tid < (int)(sizeof(ConvCloud) / 4)) { reinterpret_cast<uint32_t *>(&s_cc[b])[tid] = reinterpret_cast<const uint32_t *>(a.clouds + c)[tid]; }
     __syncthreads();

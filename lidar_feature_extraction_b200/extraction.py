@@ -172,7 +172,10 @@ class FeatureExtraction:
         self.want_curvature = want_curvature
         self.max_rings = max_rings or 128
         self._last = None
+        # owners of the input buffers of the last TWO batches: lfx_extract_batch returns before batch k's host-to-device
+        # copies have finished (two descriptor slots, lfx.h), so batch k's owners may only go when batch k+2 is enqueued
         self._keep = None
+        self._keep_prev = None
 
     # -- lifecycle
     def close(self):
@@ -226,6 +229,11 @@ class FeatureExtraction:
             data = np.ascontiguousarray(data)
             ptr, mem, nbytes = data.ctypes.data, N.LFX_MEM_HOST, data.nbytes
         n = msg.width * msg.height if msg.width else nbytes // msg.point_step
+        if msg.point_step <= 0 or n * msg.point_step > nbytes:   # an inconsistent message must not become an out-of-bounds read
+            raise ExtractionError(N.LFX_E_BAD_LAYOUT, f"width * height * point_step = {n * msg.point_step} exceeds the {nbytes} data bytes")
+        for f in (by_name["x"], by_name["y"], by_name["z"], ring):
+            if f is not None and f.offset + (4 if f is not ring else {N.LFX_RING_U8: 1, N.LFX_RING_U16: 2}.get(f.datatype, 4)) > msg.point_step:
+                raise ExtractionError(N.LFX_E_BAD_LAYOUT, f"field {f.name!r} at offset {f.offset} does not fit point_step {msg.point_step}")
         return N.CloudView(ptr, n, msg.point_step, by_name["x"].offset, by_name["y"].offset, by_name["z"].offset,
                            ring.offset if ring else 0, ring.datatype if ring else N.LFX_RING_U16,
                            1 if ring else 0, 1 if msg.is_dense else 0, mem)
@@ -257,7 +265,7 @@ class FeatureExtraction:
         res = N.BatchResult()
         self._check(self._lib.lfx_extract_batch(self._h, arr, arr.n_views, C.byref(res)))
         self._last = res
-        self._keep = keep
+        self._keep_prev, self._keep = self._keep, keep
         return res
 
     def extract_batch(self, scans: Sequence, fetch_points: bool = True) -> BatchOutput:

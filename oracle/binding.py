@@ -245,6 +245,7 @@ class Reference:
         self.variant = variant
         self.lib = L = C.CDLL(path)
         L.ref_extract_scan.argtypes = [_P, _I, C.POINTER(Params), _I] + [_P] * 7 + [_P, _P, _P, _P]
+        L.ref_color_scan.argtypes = [_P, _I, C.POINTER(Params), _P, _P]
         L.ref_polar_less.argtypes = [_F] * 4
         L.ref_curvature.argtypes = [_P, _I, _I, _P]
         L.ref_boundaries.argtypes = [_I, _I, _I, _P]
@@ -261,6 +262,16 @@ class Reference:
         assert data.size % 32 == 0
         n = data.size // 32
         return _run_scan(lambda *a: self.lib.ref_extract_scan(data.ctypes.data, n, C.byref(prm), *a), n)
+
+    def color_scan(self, cloud_bytes: np.ndarray, prm: Params):
+        """colored_scan of the reference (ColorPointsByLabel per ring, feature_extraction.cpp:153): (xyz [m, 3] f32,
+        rgb [m, 3] u8), rings ascending."""
+        data = np.ascontiguousarray(cloud_bytes).view(np.uint8).reshape(-1)
+        n = data.size // 32
+        xyz = np.zeros((max(n, 1), 3), np.float32)
+        rgb = np.zeros((max(n, 1), 3), np.uint8)
+        m = self.lib.ref_color_scan(data.ctypes.data, n, C.byref(prm), _ptr(xyz), _ptr(rgb))
+        return xyz[:m].copy(), rgb[:m].copy()
 
     def curvature(self, ranges, padding: int):
         r = np.ascontiguousarray(ranges, dtype=np.float64)

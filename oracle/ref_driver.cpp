@@ -19,6 +19,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "lidar_feature_extraction/color_points.hpp"
 #include "lidar_feature_extraction/curvature.hpp"
 #include "lidar_feature_extraction/index_range.hpp"
 #include "lidar_feature_extraction/label.hpp"
@@ -129,6 +130,51 @@ int ref_extract_scan(
   *n_edge_out = n_edge;
   *n_surface_out = n_surface;
   return n_sorted;
+}
+
+// colored_scan of one scan: the same loop, with the reference's own ColorPointsByLabel / LabelToColor
+// (color_points.hpp:60-74, color_points.cpp:39-68) appended per ring exactly where feature_extraction.cpp:153 does it
+// (inside the try block: a ring that throws contributes nothing). Rings ascending like ref_extract_scan.
+// xyz[3 * n], rgb[3 * n] (r, g, b as the reference's MakeXYZRGB assigns them). Returns the number of points.
+int ref_color_scan(const void * points, int n, const ref_params * prm, float * xyz, std::uint8_t * rgb)
+{
+  pcl::PointCloud<PointXYZIR>::Ptr input_cloud(new pcl::PointCloud<PointXYZIR>());
+  input_cloud->points.resize(n);
+  if (n > 0) {
+    std::memcpy(static_cast<void *>(input_cloud->points.data()), points, sizeof(PointXYZIR) * n);
+  }
+  const EdgeLabel edge_label(prm->padding, prm->edge_threshold);
+  const SurfaceLabel surface_label(prm->padding, prm->surface_threshold);
+  auto rings_unordered = ExtractAngleSortedRings(*input_cloud);
+  RemoveSparseRings(rings_unordered, prm->padding + 1);
+  const std::map<int, std::vector<int>> rings(rings_unordered.begin(), rings_unordered.end());
+  pcl::PointCloud<pcl::PointXYZRGB>::Ptr colored_cloud(new pcl::PointCloud<pcl::PointXYZRGB>());
+  for (const auto & [ring, indices] : rings) {
+    (void)ring;
+    try {
+      const MappedPoints<PointXYZIR> ref_points(input_cloud, indices);
+      const double radian_threshold = DegreeToRadian(prm->neighbor_degree_threshold);
+      const NeighborCheckXY<PointXYZIR> is_neighbor(ref_points, radian_threshold);
+      const Range<PointXYZIR> range(ref_points);
+      std::vector<PointLabel> lab = InitLabels(ref_points.size());
+      const std::vector<double> ranges = range(0, range.size());
+      const std::vector<double> curv = CalcCurvature(ranges, prm->padding);
+      const PaddedIndexRange index_range(range.size(), prm->n_blocks, prm->padding);
+      AssignLabel(lab, curv, is_neighbor, index_range, edge_label, surface_label);
+      LabelOccludedPoints(lab, is_neighbor, range, prm->padding, prm->distance_diff_threshold);
+      LabelOutOfRange(lab, range, prm->min_range, prm->max_range);
+      LabelParallelBeamPoints(lab, range, prm->parallel_beam_min_range_ratio);
+      *colored_cloud += *ColorPointsByLabel<PointXYZIR>(ref_points, lab);
+    } catch (const std::invalid_argument &) {
+    }
+  }
+  int m = 0;
+  for (const auto & p : colored_cloud->points) {
+    xyz[3 * m] = p.x; xyz[3 * m + 1] = p.y; xyz[3 * m + 2] = p.z;
+    rgb[3 * m] = p.r; rgb[3 * m + 1] = p.g; rgb[3 * m + 2] = p.b;
+    m++;
+  }
+  return m;
 }
 
 // Piecewise entry points used to pin the C restatement function by function.

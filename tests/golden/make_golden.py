@@ -70,6 +70,8 @@ def main():
             r = ref.extract_scan(cloud, ob.default_params(**kw))
             for f in ("ring_ids", "ring_sizes", "ring_skipped", "sorted_src", "labels", "curvature", "edge_idx", "surface_idx"):
                 out[f"{pname}.{f}"] = np.asarray(getattr(r, f))
+            # colored_scan by the reference's own ColorPointsByLabel (ref_color_scan): x,y,z and r,g,b per point
+            out[f"{pname}.colored_xyz"], out[f"{pname}.colored_rgb"] = ref.color_scan(cloud, ob.default_params(**kw))
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
         print(f"{name}: {len(cloud)} points -> {os.path.getsize(path) / 1024:.0f} KiB")

@@ -139,3 +139,69 @@ int main() {
                     f"-L{pkg}", "-llfx", f"-Wl,-rpath,{pkg}"], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == (0 if torch.cuda.is_available() else 42), (r.returncode, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_extracts_a_scan_on_the_gpu(tmp_path):
+    """The success path of include/lfx.hpp on the device: a C++ program (no Python, no ctypes) feeds one VLP-16-shaped
+    scan through lfx::FeatureExtraction::Extract and ColoredScan; its clouds and labels must equal the oracle's."""
+    import shutil
+    import subprocess
+
+    from lidar_feature_extraction_b200 import synth
+    from oracle import binding as ob
+    from oracle import color_oracle as co
+
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cloud = synth.scan_host(synth.spec("vlp16"), frame=5)
+    (tmp_path / "scan.bin").write_bytes(cloud.tobytes())
+    src = tmp_path / "host.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <fstream>
+#include <iterator>
+#include "lfx.hpp"
+static void dump(const char * path, const void * p, size_t n) { std::ofstream f(path, std::ios::binary); f.write(static_cast<const char *>(p), n); }
+int main(int argc, char ** argv) {
+  std::ifstream in(argv[1], std::ios::binary);
+  std::vector<char> bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  const std::vector<lfx::PointField> f = {{"x", 0, 7}, {"y", 4, 7}, {"z", 8, 7}, {"intensity", 16, 7}, {"ring", 20, LFX_RING_U16}};
+  try {
+    lfx_options opt;
+    std::memset(&opt, 0, sizeof(opt));
+    opt.want_sorted_src = 1;                                            // colored_scan needs the index map
+    lfx::FeatureExtraction fe(lfx::HyperParameters(), opt);
+    const lfx_cloud_view v = lfx::MakeView(bytes.data(), (uint32_t)(bytes.size() / 32), 32, f, true);
+    const lfx_scan_output out = fe.Extract(v);
+    dump(argv[2], out.edge_xyz, 16 * (size_t)out.n_edge);
+    dump(argv[3], out.surface_xyz, 16 * (size_t)out.n_surface);
+    dump(argv[4], out.labels, out.n_points);
+    const std::vector<uint8_t> colored = fe.ColoredScan(0);
+    dump(argv[5], colored.data(), colored.size());
+    std::printf("%u %u %u\n", out.n_points, out.n_edge, out.n_surface);
+    return 0;
+  } catch (const lfx::Error & e) {
+    std::printf("error %d: %s\n", e.code, e.what());
+    return 14;
+  }
+}
+''')
+    exe = tmp_path / "host"
+    pkg = os.path.join(root, "lidar_feature_extraction_b200")
+    subprocess.run([cxx, "-std=c++17", "-Wall", "-Werror", f"-I{root}/include", str(src), "-o", str(exe),
+                    f"-L{pkg}", "-llfx", f"-Wl,-rpath,{pkg}"], check=True)
+    outs = [str(tmp_path / n) for n in ("edge.bin", "surface.bin", "labels.bin", "colored.bin")]
+    r = subprocess.run([str(exe), str(tmp_path / "scan.bin")] + outs, capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    ref = ob.Oracle().extract_scan(cloud, ob.default_params())
+    x, y, z, _, _ = (np.ascontiguousarray(a) for a in synth.fields(cloud))
+    src_idx = ref.sorted_src
+    for path, idx in ((outs[0], ref.edge_idx), (outs[1], ref.surface_idx)):
+        got = np.fromfile(path, np.float32).reshape(-1, 4)
+        want = np.stack([x[src_idx[idx]], y[src_idx[idx]], z[src_idx[idx]], np.ones(len(idx), np.float32)], axis=1)
+        assert np.array_equal(got, want)
+    assert np.array_equal(np.fromfile(outs[2], np.uint8), ref.labels)
+    assert np.array_equal(np.fromfile(outs[3], np.uint8).reshape(-1, 32), co.colored_scan(x, y, z, ref))
