@@ -275,6 +275,12 @@ int lfx_convert_batch(lfx_handle *h, const lfx_raw_cloud *clouds, int n_clouds, 
 int lfx_last_convert_ms(lfx_handle *h, float *ms);
 /* View of converted cloud `cloud` (device memory, deployed layout) ready for lfx_extract_batch. */
 int lfx_converted_view(lfx_handle *h, int cloud, lfx_cloud_view *out);
+/* All successfully converted clouds of the last lfx_convert_batch at once, in cloud order (clouds for which the
+ * reference's callback raises are left out, as nothing is published for them): out[capacity], *n_out views. This is
+ * the array to hand to lfx_extract_batch for the deployed chain /points_raw -> converter -> extraction. The ring
+ * ids of these clouds are also kept as a compact by-product of the conversion, which lfx_extract_batch uses when it
+ * has to bucket them (the clouds must not be modified in between). */
+int lfx_converted_views(lfx_handle *h, lfx_cloud_view *out, int capacity, int *n_out);
 /* Copies converted cloud `cloud` (32 * kept bytes = PointCloud2.data of /points_converted) to host memory. */
 int lfx_fetch_converted(lfx_handle *h, int cloud, void *dst, size_t capacity_bytes);
 

@@ -169,6 +169,16 @@ public:
     if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); }
     return v;
   }
+  // views of every successfully converted cloud of the last Convert, in cloud order: the argument of ExtractBatch
+  std::vector<lfx_cloud_view> Views(int n_clouds)
+  {
+    std::vector<lfx_cloud_view> v(static_cast<size_t>(n_clouds > 0 ? n_clouds : 1));
+    int n = 0;
+    const int rc = lfx_converted_views(h_, v.data(), n_clouds, &n);
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); }
+    v.resize(static_cast<size_t>(n));
+    return v;
+  }
   // PointCloud2.data of /points_converted (convert.py:198-212: point_step 32, height 1, width = size / 32, is_dense)
   std::vector<uint8_t> Fetch(int cloud, uint32_t kept)
   {

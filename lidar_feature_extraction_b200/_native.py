@@ -229,6 +229,7 @@ def lib() -> C.CDLL:
     L.lfx_convert_batch.argtypes = [H, C.POINTER(RawCloud), C.c_int, C.POINTER(ConvertResult)]
     L.lfx_last_convert_ms.argtypes = [H, C.POINTER(C.c_float)]
     L.lfx_converted_view.argtypes = [H, C.c_int, C.POINTER(CloudView)]
+    L.lfx_converted_views.argtypes = [H, C.POINTER(CloudView), C.c_int, C.POINTER(C.c_int)]
     L.lfx_fetch_converted.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     L.lfx_color_batch.argtypes = [H, C.POINTER(ColoredResult)]
     L.lfx_fetch_colored.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]

@@ -54,10 +54,41 @@ class PointTypeConverter:
         self.close()
 
     # -- batched entry
-    def convert_batch(self, msgs: Sequence[PointCloud2]) -> N.ConvertResult:
-        """One launch for all clouds. Returns the lfx_convert_result (device pointers + per-cloud status);
-        does not raise for per-cloud failures - see ``status_of`` / ``fetch``."""
+    def marshal(self, msgs: Sequence[PointCloud2]):
+        """The C array of lfx_raw_cloud for ``msgs`` (with the Python owners of everything it points to). Build it once
+        when the same messages are converted repeatedly: marshalling a thousand structs costs milliseconds."""
+        keep, raws = self._marshal(msgs)
+        carr = (N.RawCloud * max(len(raws), 1))(*raws)
+        carr.n_clouds = len(raws)
+        carr.keep = keep
+        return carr
+
+    def convert_batch(self, msgs) -> N.ConvertResult:
+        """One launch for all clouds (``msgs``: PointCloud2 messages, or the result of ``marshal``). Returns the
+        lfx_convert_result (device pointers + per-cloud status); does not raise for per-cloud failures - see
+        ``status_of`` / ``fetch``."""
         h = self.extraction.handle
+        carr = msgs if hasattr(msgs, "n_clouds") else self.marshal(msgs)
+        res = N.ConvertResult()
+        rc = self._lib.lfx_convert_batch(h, carr, carr.n_clouds, C.byref(res))
+        if rc not in (N.LFX_OK, N.LFX_E_CONVERT):
+            raise ExtractionError(rc, self._lib.lfx_last_error(h).decode())
+        self._keep = carr
+        self._res = res
+        return res
+
+    def views(self):
+        """view_array of every successfully converted cloud of the last batch (one C call), for ``extract_views``."""
+        n = len(self._keep.keep) if self._keep is not None else 0
+        arr = (N.CloudView * max(n, 1))()
+        got = C.c_int(0)
+        rc = self._lib.lfx_converted_views(self.extraction.handle, arr, n, C.byref(got))
+        if rc != N.LFX_OK:
+            raise ExtractionError(rc, self._lib.lfx_last_error(self.extraction.handle).decode())
+        arr.n_views = got.value
+        return arr
+
+    def _marshal(self, msgs: Sequence[PointCloud2]):
         keep, raws = [], []
         field_cache = {}   # clouds of one driver share their field table: marshal it once
         for m in msgs:
@@ -76,14 +107,7 @@ class PointTypeConverter:
                 ptr, nbytes, mem = data.ctypes.data, data.nbytes, N.LFX_MEM_HOST
             keep.append((names, arr, data, m.fields))
             raws.append(N.RawCloud(ptr, nbytes, m.point_step, arr, nf, 1 if m.is_bigendian else 0, mem))
-        res = N.ConvertResult()
-        carr = (N.RawCloud * max(len(raws), 1))(*raws)
-        rc = self._lib.lfx_convert_batch(h, carr, len(raws), C.byref(res))
-        if rc not in (N.LFX_OK, N.LFX_E_CONVERT):
-            raise ExtractionError(rc, self._lib.lfx_last_error(h).decode())
-        self._keep = keep
-        self._res = res
-        return res
+        return keep, raws
 
     def status_of(self, cloud: int) -> int:
         return int(self._res.status[cloud])

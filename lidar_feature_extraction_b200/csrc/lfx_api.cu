@@ -88,8 +88,6 @@ struct lfx_handle
   DevBuf<uint2> d_ring_src;
   DevBuf<uint32_t> d_scan_flags;
   DevBuf<uint32_t> d_gen_scan, d_gen_tile_base, d_tile_owner;
-  bool scatter_bm = false;   // bitmap scatter (max_rings small enough for shared memory)
-  int scatter_bm_grid = 0;
   DevBuf<FastRing> d_fast[2 * N_FAST_K];
   DevBuf<SectorRec> d_rec[2 * N_FAST_K];
   DevBuf<int> d_bndx[N_FAST_K];
@@ -104,6 +102,7 @@ struct lfx_handle
   uint32_t * d_counters = nullptr;
   // upstream converter (lfx_convert_batch)
   DevBuf<uint8_t> d_conv_raw, d_conv_out;
+  DevBuf<uint16_t> d_conv_ring16;   // ring id of every converted point (k_convert by-product)
   DevBuf<ConvCloud> d_conv_clouds;
   DevBuf<unsigned long long> d_conv_state;
   DevBuf<uint32_t> d_conv_meta;     // ticket | kept[n] | flags[n]
@@ -330,15 +329,8 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
     h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
   k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
     h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, max_rings, h->params.padding, h->cap);
-  if (h->scatter_bm) {
-    const int grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_tiles, 1u), (uint32_t)h->scatter_bm_grid);
-    k_ring_scatter_bm<<<grid, INGEST_THREADS, scatter_bm_smem(max_rings), h->stream>>>(
-      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p,
-      h->d_rings.p, h->d_idx.p, max_rings);
-  } else {
-    k_ring_scatter<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * (INGEST_THREADS / 32) * max_rings, h->stream>>>(
-      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
-  }
+  k_ring_scatter<<<ingest_grid, INGEST_THREADS, scatter_smem_bytes(max_rings), h->stream>>>(
+    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
   // ---- bucketed rings that are rotated monotone sequences: sector kernel through the index list; the rest
   //      (and every ring whose hypothesis fails there) form the work list of the per-ring kernel
   RingProbeArgs rp;
@@ -531,19 +523,12 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   int tmax = 0;
   h->ring_kernel = pick_ring_kernel(params->padding, h->ring_threads, &tmax);
   if ((e = cudaFuncSetAttribute(h->ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ring_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(rings)"); }
-  const size_t scatter_smem = sizeof(uint32_t) * (INGEST_THREADS / 32) * h->opt.max_rings;
+  const size_t scatter_smem = scatter_smem_bytes(h->opt.max_rings);
   if (scatter_smem > 48 * 1024) {
     if ((e = cudaFuncSetAttribute(k_ring_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter)"); }
   }
   int occ = 0;
   // bitmap scatter: 390 B of shared memory per ring id; above ~500 ring ids the match-based scatter takes over
-  h->scatter_bm = h->opt.max_rings % 4 == 0 && scatter_bm_smem(h->opt.max_rings) <= (size_t)prop.sharedMemPerBlockOptin;
-  if (h->scatter_bm) {
-    const size_t sb = scatter_bm_smem(h->opt.max_rings);
-    if ((e = cudaFuncSetAttribute(k_ring_scatter_bm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter_bm)"); }
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ring_scatter_bm, INGEST_THREADS, sb)) != cudaSuccess) { return bail(e, "occupancy(scatter_bm)"); }
-    h->scatter_bm_grid = h->num_sms * std::max(occ, 1);
-  }
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->ring_kernel, h->ring_threads, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
   h->ring_grid = h->num_sms * std::max(occ, 1);
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_copy, 256, 0)) != cudaSuccess) { return bail(e, "occupancy(pack)"); }
@@ -598,7 +583,7 @@ void lfx_destroy(lfx_handle * h)
   for (int c = 0; c < 2 * N_FAST_K; c++) { cudaFree(h->d_fast[c].p); cudaFree(h->d_rec[c].p); }
   for (int c = 0; c < N_FAST_K; c++) { cudaFree(h->d_bndx[c].p); }
   cudaFree(h->d_ring_path.p);
-  cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p); cudaFree(h->d_conv_tile_cloud.p);
+  cudaFree(h->d_conv_raw.p); cudaFree(h->d_conv_out.p); cudaFree(h->d_conv_ring16.p); cudaFree(h->d_conv_clouds.p); cudaFree(h->d_conv_state.p); cudaFree(h->d_conv_meta.p); cudaFree(h->d_conv_tile_cloud.p);
   cudaFree(h->d_colored.p); cudaFree(h->d_colored_counts.p);
   cudaFree(h->d_map.p); cudaFree(h->d_map_frames.p);
   for (auto & ev : h->conv_ev) { if (ev) { cudaEventDestroy(ev); } }
@@ -754,7 +739,16 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
     d.ring_dt = v.ring_datatype;
     d.tile_base = tb;
     d.n_tiles = (v.n_points + TILE - 1) / TILE;
-    d.reserved[0] = d.reserved[1] = 0;
+    d.ring16_lo = d.ring16_hi = 0;
+    if (v.memory != LFX_MEM_HOST && h->have_conv && h->d_conv_out.p && v.point_step == 32 && v.off_ring == 20 && v.ring_datatype == LFX_RING_U16) {
+      // a cloud the converter of this handle has just produced: its ring ids exist as a compact u16 array
+      const uint8_t * p0 = static_cast<const uint8_t *>(v.data);
+      const uint8_t * lo = h->d_conv_out.p, * hi = h->d_conv_out.p + h->conv_point_base.back() * 32;
+      if (p0 >= lo && p0 + bytes <= hi && ((p0 - lo) & 31) == 0) {
+        const uint64_t a16 = reinterpret_cast<uint64_t>(h->d_conv_ring16.p + ((p0 - lo) >> 5));
+        d.ring16_lo = (uint32_t)a16; d.ring16_hi = (uint32_t)(a16 >> 32);
+      }
+    }
     d.vec_ok = (v.off_y == v.off_x + 4 && v.off_z == v.off_x + 8 && v.off_x % 16 == 0 && v.point_step % 16 == 0 &&
                 v.off_x + 16 <= v.point_step && reinterpret_cast<uintptr_t>(d.data) % 16 == 0) ? 1u : 0u;
     h->h_point_base[s] = pb;
@@ -1204,6 +1198,7 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
     int rc;
     if ((rc = ensure(h, h->d_conv_raw, (size_t)host_bytes + 256, nullptr))) { return rc; }
     if ((rc = ensure(h, h->d_conv_out, (size_t)points * 32 + 32, nullptr))) { return rc; }
+    if ((rc = ensure(h, h->d_conv_ring16, (size_t)points + 32, nullptr))) { return rc; }
     if ((rc = ensure(h, h->d_conv_clouds, (size_t)n_clouds, nullptr))) { return rc; }
     if ((rc = ensure(h, h->d_conv_state, (size_t)tiles, nullptr))) { return rc; }
     if ((rc = ensure(h, h->d_conv_tile_cloud, (size_t)tiles, nullptr))) { return rc; }
@@ -1235,6 +1230,8 @@ int lfx_convert_batch(lfx_handle * h, const lfx_raw_cloud * clouds, int n_clouds
     a.ticket = h->d_conv_meta.p;
     a.kept = h->d_conv_meta.p + 1;
     a.flags = h->d_conv_meta.p + 1 + n_clouds;
+    a.out_base = h->d_conv_out.p;
+    a.ring16 = h->d_conv_ring16.p;
     if (!h->conv_smem_set) {
       LFX_CUDA(h, cudaFuncSetAttribute(k_convert<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_STAGE_MAX_BYTES));
       LFX_CUDA(h, cudaFuncSetAttribute(k_convert<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_STAGE_MAX_BYTES));
@@ -1307,6 +1304,22 @@ int lfx_converted_view(lfx_handle * h, int cloud, lfx_cloud_view * out)
   out->has_ring = 1;
   out->is_dense = 1;                            // convert.py:210
   out->memory = LFX_MEM_DEVICE;
+  return LFX_OK;
+}
+
+int lfx_converted_views(lfx_handle * h, lfx_cloud_view * out, int capacity, int * n_out)
+{
+  if (!h || !out || !n_out) { return LFX_E_BAD_PARAM; }
+  if (!h->have_conv) { return fail(h, LFX_E_STATE, "no batch has been converted"); }
+  int n = 0;
+  for (size_t c = 0; c < h->conv_kept.size(); c++) {
+    if (h->conv_status[c] != LFX_CONVERT_OK) { continue; }   // the reference's callback raises for this cloud: nothing is published
+    if (n >= capacity) { return fail(h, LFX_E_CAPACITY, "more converted clouds than view slots"); }
+    const int rc = lfx_converted_view(h, (int)c, &out[n]);
+    if (rc != LFX_OK) { return rc; }
+    n++;
+  }
+  *n_out = n;
   return LFX_OK;
 }
 

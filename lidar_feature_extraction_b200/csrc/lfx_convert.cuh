@@ -65,6 +65,9 @@ struct ConvArgs
   uint32_t * ticket;
   uint32_t * kept;                  // [n_clouds]
   uint32_t * flags;                 // [n_clouds]
+  const uint8_t * out_base;         // first byte of the output buffer (ConvCloud::out points into it)
+  uint16_t * ring16;                // by-product: the ring id of output point i of the buffer at [i] (lfx_extract_batch's
+                                    // bucketing reads these 2 bytes per point instead of the points' 32-byte sectors)
 };
 
 __device__ __forceinline__ int conv_size(uint32_t dt) { return dt <= 2 ? 1 : (dt <= 4 ? 2 : (dt <= 7 ? 4 : 8)); }
@@ -333,6 +336,7 @@ k_convert(const ConvArgs a)
         uint4 * dst = reinterpret_cast<uint4 *>(cc.out + (size_t)(excl + rank) * 32);
         __stcs(dst, make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]));
         __stcs(dst + 1, make_uint4(w[i][4], w[i][5], 0u, 0u));
+        a.ring16[(size_t)((cc.out - a.out_base) >> 5) + (size_t)(excl + rank)] = (uint16_t)w[i][5];
       }
       if (overflow || range) { atomicOr(&a.flags[c], (overflow ? CONV_F_OVERFLOW : 0u) | (range ? CONV_F_RING_RANGE : 0u)); }
     }

@@ -53,8 +53,15 @@ struct ScanDesc
   uint32_t tile_base;   // first ingest tile of this scan
   uint32_t n_tiles;
   uint32_t vec_ok;      // xyz loadable as one aligned float4
-  uint32_t reserved[2]; // pads the descriptor to 64 bytes (copied with 16-byte cp.async)
+  uint32_t ring16_lo, ring16_hi;   // optional: address of a u16 ring id per point (converter by-product), else 0
+                                   // (two words: the descriptor stays 64 bytes, copied with 16-byte cp.async)
 };
+static_assert(sizeof(ScanDesc) == 64, "ScanDesc is copied as four 16-byte chunks");
+
+__host__ __device__ inline const uint16_t * scan_ring16(const ScanDesc & sd)
+{
+  return reinterpret_cast<const uint16_t *>((uint64_t)sd.ring16_lo | ((uint64_t)sd.ring16_hi << 32));
+}
 
 struct DevParams
 {
@@ -170,12 +177,40 @@ k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t 
       const uint32_t k = carry_c + s_c[tid] - 1, tb = carry_t + s_t[tid] - nt;
       gen_scan[k] = (uint32_t)i;
       gen_tile_base[k] = tb;
-      for (uint32_t j = 0; j < nt; j++) { tile_owner[tb + j] = k; }   // general tile -> its entry of gen_scan
     }
     carry_c += s_c[1023]; carry_t += s_t[1023];
     __syncthreads();
   }
   if (tid == 0) { gen_tile_base[carry_c] = carry_t; counters[C_GEN_SCANS] = carry_c; counters[C_GEN_TILES] = carry_t; }
+  __syncthreads();
+  // general tile -> its entry of gen_scan, one flagged scan after the other with the whole CTA on its tiles (coalesced)
+  for (uint32_t k = 0; k < carry_c; k++) {
+    const uint32_t tb = gen_tile_base[k], te = gen_tile_base[k + 1];
+    for (uint32_t j = tb + tid; j < te; j += 1024) { tile_owner[j] = k; }
+  }
+}
+
+// descriptor of general tile t (three dependent loads: owner -> scan -> ScanDesc), fetched one tile ahead by the
+// kernels below so that the chain runs while the current tile is processed
+struct TileJob { uint32_t scan, tile, first, n_points; uint64_t point_base; const uint8_t * ring_ptr; uint32_t point_step, ring_dt; const uint16_t * src16; };
+
+__device__ __forceinline__ TileJob load_tile_job(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
+                                                 const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner, uint32_t t)
+{
+  const uint32_t k = tile_owner[t];
+  TileJob j;
+  j.scan = gen_scan[k];
+  const uint32_t in_scan = t - gen_tile_base[k];
+  const ScanDesc & sd = scans[j.scan];
+  j.tile = sd.tile_base + in_scan;
+  j.first = in_scan * TILE;
+  j.n_points = sd.n_points;
+  j.point_base = sd.point_base;
+  j.ring_ptr = sd.data + sd.off_ring;
+  j.point_step = sd.point_step;
+  j.ring_dt = sd.ring_dt;
+  j.src16 = scan_ring16(sd);
+  return j;
 }
 
 __global__ void __launch_bounds__(INGEST_THREADS)
@@ -184,35 +219,41 @@ k_ring_hist(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ g
             uint32_t * __restrict__ tile_hist, int max_rings, uint32_t * counters)
 {
   extern __shared__ uint32_t s_hist[];
-  __shared__ int s_scan;
-  __shared__ uint32_t s_tile;
+  constexpr int PER = TILE / INGEST_THREADS;   // 8 points per thread: i = c * 256 + tid
+  const int tid = threadIdx.x;
   const uint32_t n_tiles = counters[C_GEN_TILES];
-  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t k = tile_owner[t];
-      s_scan = (int)gen_scan[k];
-      s_tile = scans[s_scan].tile_base + (t - gen_tile_base[k]);
-    }
-    for (int r = threadIdx.x; r < max_rings; r += blockDim.x) { s_hist[r] = 0; }
-    __syncthreads();
-    const ScanDesc sd = scans[s_scan];
-    const uint32_t tile = s_tile;
-    const uint32_t first = (tile - sd.tile_base) * TILE;
-    for (uint32_t k = threadIdx.x; k < TILE; k += blockDim.x) {
-      const uint32_t i = first + k;
-      if (i < sd.n_points) {
-        uint32_t ring = load_ring_id(sd.data + (size_t)i * sd.point_step + sd.off_ring, sd.ring_dt);
-        if (ring >= (uint32_t)max_rings) {
-          if (atomicExch(&counters[C_ERR_FLAG], LFX_E_CAPACITY) == 0) { counters[C_ERR_SCAN] = s_scan; counters[C_ERR_RING] = ring; }
-          ring = max_rings - 1;
-        }
-        ring16[sd.point_base + i] = (uint16_t)ring;
-        atomicAdd(&s_hist[ring], 1u);
+  uint32_t t = blockIdx.x;
+  if (t >= n_tiles) { return; }
+  TileJob cur = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, t);
+  for (; t < n_tiles; t += gridDim.x) {
+    const uint32_t tn = t + gridDim.x < n_tiles ? t + gridDim.x : t;
+    const TileJob nxt = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, tn);
+    uint32_t rg[PER];
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      const uint32_t i = cur.first + c * INGEST_THREADS + tid;
+      rg[c] = 0xFFFFFFFFu;
+      if (i < cur.n_points) {
+        rg[c] = cur.src16 ? (uint32_t)cur.src16[i] : load_ring_id(cur.ring_ptr + (size_t)i * cur.point_step, cur.ring_dt);
       }
     }
+    __syncthreads();   // the previous tile's histogram has been written out
+    for (int r = tid; r < max_rings; r += INGEST_THREADS) { s_hist[r] = 0; }
     __syncthreads();
-    for (int r = threadIdx.x; r < max_rings; r += blockDim.x) { tile_hist[(size_t)tile * max_rings + r] = s_hist[r]; }
+#pragma unroll
+    for (int c = 0; c < PER; c++) {
+      if (rg[c] == 0xFFFFFFFFu) { continue; }
+      uint32_t ring = rg[c];
+      if (ring >= (uint32_t)max_rings) {
+        if (atomicExch(&counters[C_ERR_FLAG], LFX_E_CAPACITY) == 0) { counters[C_ERR_SCAN] = cur.scan; counters[C_ERR_RING] = ring; }
+        ring = max_rings - 1;
+      }
+      if (!cur.src16) { ring16[cur.point_base + cur.first + c * INGEST_THREADS + tid] = (uint16_t)ring; }
+      atomicAdd(&s_hist[ring], 1u);
+    }
+    __syncthreads();
+    for (int r = tid; r < max_rings; r += INGEST_THREADS) { tile_hist[(size_t)cur.tile * max_rings + r] = s_hist[r]; }
+    cur = nxt;
   }
 }
 
@@ -229,11 +270,19 @@ k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ s
   const ScanDesc sd = scans[scan];
   for (int r = threadIdx.x; r < max_rings; r += blockDim.x) {
     uint32_t run = 0;
-    for (uint32_t t = 0; t < sd.n_tiles; t++) {
-      uint32_t * h = &tile_hist[(size_t)(sd.tile_base + t) * max_rings + r];
-      const uint32_t c = *h;
-      *h = run;  // exclusive prefix over the scan's tiles: stable bucket base of this tile
-      run += c;
+    // exclusive prefix over the scan's tiles: stable bucket base of every tile. Eight loads are issued before the
+    // first store (the compiler cannot prove that the stores do not alias the next loads and would serialise them).
+    for (uint32_t t0 = 0; t0 < sd.n_tiles; t0 += 8) {
+      uint32_t c[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        c[u] = t0 + u < sd.n_tiles ? tile_hist[(size_t)(sd.tile_base + t0 + u) * max_rings + r] : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (t0 + u < sd.n_tiles) { tile_hist[(size_t)(sd.tile_base + t0 + u) * max_rings + r] = run; }
+        run += c[u];
+      }
     }
     s_cnt[r] = run;
   }
@@ -258,158 +307,120 @@ k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ s
 
 // ------------------------------------------------------------------ ingest: stable scatter (one CTA per tile)
 
+// shared memory: [8 warps][R] positions | [R] tile count | [R] tile offset | [R] bucket base | [TILE] sorted source
+// indices | [TILE] their rings (u16) | [8 warps][R] lane probes (bytes)
+__host__ __device__ inline size_t scatter_smem_bytes(int max_rings)
+{
+  return (size_t)(INGEST_THREADS / 32) * max_rings * 5 + (size_t)max_rings * 12 + (size_t)TILE * 6;
+}
+
 __global__ void __launch_bounds__(INGEST_THREADS)
 k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
-               const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ counters,
+               const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner,
+               const uint32_t * __restrict__ counters,
                const uint16_t * __restrict__ ring16, const uint32_t * __restrict__ tile_hist,
                const lfx_ring_info * __restrict__ rings, uint32_t * __restrict__ idx, int max_rings)
 {
-  extern __shared__ uint32_t s_base[];  // [8 warps][max_rings]
-  __shared__ int s_scan;
-  __shared__ uint32_t s_tile;
+  extern __shared__ uint32_t s_base[];
   constexpr int WARPS = INGEST_THREADS / 32;
   constexpr int PER_WARP = TILE / WARPS;   // 256 consecutive points
   constexpr int CHUNKS = PER_WARP / 32;    // 8
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n_tiles = counters[C_GEN_TILES];
-  const int n_gen = (int)counters[C_GEN_SCANS];
-  for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int k = find_gen_scan(gen_tile_base, n_gen, t);
-      s_scan = (int)gen_scan[k];
-      s_tile = scans[s_scan].tile_base + (t - gen_tile_base[k]);
-    }
-    for (int r = threadIdx.x; r < WARPS * max_rings; r += blockDim.x) { s_base[r] = 0; }
-    __syncthreads();
-    const int scan = s_scan;
-    const uint32_t tile = s_tile;
-    const ScanDesc sd = scans[scan];
-    const uint32_t first = (tile - sd.tile_base) * TILE + warp * PER_WARP;
-    uint32_t * my = s_base + warp * max_rings;
-
-    uint32_t ring[CHUNKS];
-#pragma unroll
-    for (int c = 0; c < CHUNKS; c++) {
-      const uint32_t i = first + c * 32 + lane;
-      ring[c] = i < sd.n_points ? (uint32_t)ring16[sd.point_base + i] : 0xFFFFFFFFu;
-      if (ring[c] != 0xFFFFFFFFu) { atomicAdd(&my[ring[c]], 1u); }
-    }
-    __syncthreads();
-    // per ring: running prefix over the 8 warps, seeded with the tile's stable base inside the ring bucket
-    for (int r = threadIdx.x; r < max_rings; r += blockDim.x) {
-      uint32_t run = rings[(size_t)scan * max_rings + r].offset + tile_hist[(size_t)tile * max_rings + r];
-      for (int w = 0; w < WARPS; w++) {
-        const uint32_t c = s_base[w * max_rings + r];
-        s_base[w * max_rings + r] = run;
-        run += c;
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < CHUNKS; c++) {
-      const uint32_t i = first + c * 32 + lane;
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ring[c]);
-      if (ring[c] != 0xFFFFFFFFu) {
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        const uint32_t base = my[ring[c]];
-        __syncwarp(peers);
-        if (rank == 0) { my[ring[c]] = base + __popc(peers); }
-        idx[sd.point_base + base + rank] = i;
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// ------------------------------------------------------------------ ingest: stable scatter through ring bitmaps
-//
-// The same stable scatter without warp match operations (a warp of 32 consecutive points in firing order holds
-// 32 distinct ring ids, the slowest case of match.any) and without a serial chain per tile: every point sets
-// its bit in the bitmap of its ring (shared memory, word-major so that a warp's 32 rings hit 32 banks); the
-// rank of a point inside its ring's run of this tile is the number of set bits before it.
-constexpr int BM_WORDS = TILE / 32;
-
-__host__ __device__ inline size_t scatter_bm_smem(int max_rings)
-{
-  return (size_t)max_rings * BM_WORDS * 4 + (size_t)max_rings * BM_WORDS * 2 + (size_t)max_rings * 4;
-}
-
-struct TileJob { uint32_t scan, tile, first, n_points; uint64_t point_base; };
-
-__device__ __forceinline__ TileJob load_tile_job(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
-                                                 const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner, uint32_t t)
-{
-  const uint32_t k = tile_owner[t];
-  TileJob j;
-  j.scan = gen_scan[k];
-  const uint32_t in_scan = t - gen_tile_base[k];
-  const ScanDesc & sd = scans[j.scan];
-  j.tile = sd.tile_base + in_scan;
-  j.first = in_scan * TILE;
-  j.n_points = sd.n_points;
-  j.point_base = sd.point_base;
-  return j;
-}
-
-__global__ void __launch_bounds__(INGEST_THREADS)
-k_ring_scatter_bm(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
-                  const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner,
-                  const uint32_t * __restrict__ counters, const uint16_t * __restrict__ ring16,
-                  const uint32_t * __restrict__ tile_hist, const lfx_ring_info * __restrict__ rings,
-                  uint32_t * __restrict__ idx, int max_rings)
-{
-  extern __shared__ __align__(16) unsigned char bm_raw[];
-  const int R = max_rings;
-  uint32_t * bm = reinterpret_cast<uint32_t *>(bm_raw);               // [BM_WORDS][R]
-  uint16_t * pre = reinterpret_cast<uint16_t *>(bm + (size_t)R * BM_WORDS);   // [BM_WORDS][R] set bits in earlier words
-  uint32_t * rbase = reinterpret_cast<uint32_t *>(pre + (size_t)R * BM_WORDS); // [R] bucket position of the ring's run
-  constexpr int PER = TILE / INGEST_THREADS;   // 8 points per thread: i = c * 256 + tid
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, R = max_rings;
   const uint32_t n_tiles = counters[C_GEN_TILES];
   uint32_t t = blockIdx.x;
   if (t >= n_tiles) { return; }
+  uint32_t * my = s_base + warp * R;
+  uint32_t * tcount = s_base + WARPS * R;
+  uint32_t * toff = tcount + R;
+  uint32_t * gbase = toff + R;
+  uint32_t * s_out = gbase + R;
+  uint16_t * s_ring = reinterpret_cast<uint16_t *>(s_out + TILE);
+  uint8_t * probe = reinterpret_cast<uint8_t *>(s_ring + TILE) + warp * R;
+  __shared__ uint32_t s_total;
   TileJob cur = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, t);
   for (; t < n_tiles; t += gridDim.x) {
     // the next tile's descriptor chain (three dependent loads) runs while this tile is processed
     const uint32_t tn = t + gridDim.x < n_tiles ? t + gridDim.x : t;
     const TileJob nxt = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, tn);
-    uint32_t rg[PER];
+    const uint16_t * src16 = cur.src16 ? cur.src16 : ring16 + cur.point_base;   // converter by-product, else k_ring_hist's copy
+    const uint32_t first = cur.first + warp * PER_WARP;
+    uint32_t ring[CHUNKS];
 #pragma unroll
-    for (int c = 0; c < PER; c++) {
-      const uint32_t i = cur.first + c * INGEST_THREADS + tid;
-      rg[c] = i < cur.n_points ? (uint32_t)ring16[cur.point_base + i] : 0xFFFFFFFFu;
+    for (int c = 0; c < CHUNKS; c++) {
+      const uint32_t i = first + c * 32 + lane;
+      ring[c] = i < cur.n_points ? (uint32_t)src16[i] : 0xFFFFFFFFu;
     }
-    __syncthreads();   // the previous tile's bitmaps are no longer read
-    for (int r = tid; r < R; r += INGEST_THREADS) {
-      rbase[r] = rings[(size_t)cur.scan * R + r].offset + tile_hist[(size_t)cur.tile * R + r];
-    }
-    {
-      uint4 * z = reinterpret_cast<uint4 *>(bm);
-      for (int k = tid; k < R * BM_WORDS / 4; k += INGEST_THREADS) { z[k] = make_uint4(0u, 0u, 0u, 0u); }
-    }
+    __syncthreads();   // the previous tile's arrays are no longer used
+    for (int r = threadIdx.x; r < WARPS * R; r += blockDim.x) { s_base[r] = 0; }
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < PER; c++) {
-      if (rg[c] != 0xFFFFFFFFu) { atomicOr(&bm[(c * (INGEST_THREADS / 32) + (tid >> 5)) * R + rg[c]], 1u << lane); }
+    for (int c = 0; c < CHUNKS; c++) {
+      if (ring[c] != 0xFFFFFFFFu) { atomicAdd(&my[ring[c]], 1u); }
     }
     __syncthreads();
-    for (int r = tid; r < R; r += INGEST_THREADS) {
+    // per ring: running prefix over the 8 warps (position inside the ring's run of this tile), the run's length, and
+    // where the run goes: the tile's stable base inside the ring bucket
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
       uint32_t run = 0;
-#pragma unroll 8
-      for (int w = 0; w < BM_WORDS; w++) {
-        pre[w * R + r] = (uint16_t)run;
-        run += __popc(bm[w * R + r]);
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) {
+        const uint32_t c = s_base[w * R + r];
+        s_base[w * R + r] = run;
+        run += c;
       }
+      tcount[r] = run;
+      gbase[r] = run ? rings[(size_t)cur.scan * R + r].offset + tile_hist[(size_t)cur.tile * R + r] : 0u;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive prefix of the run lengths over the rings: the runs' places in the staging array
+      uint32_t carry = 0;
+      for (int r0 = 0; r0 < R; r0 += 32) {
+        const uint32_t v = r0 + lane < R ? tcount[r0 + lane] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) { inc += u; } }
+        if (r0 + lane < R) { toff[r0 + lane] = carry + inc - v; }
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+      }
+      if (lane == 0) { s_total = carry; }
     }
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < PER; c++) {
-      if (rg[c] != 0xFFFFFFFFu) {
-        const int w = c * (INGEST_THREADS / 32) + (tid >> 5);
-        const uint32_t rank = pre[w * R + rg[c]] + __popc(bm[w * R + rg[c]] & ((1u << lane) - 1u));
-        idx[cur.point_base + rbase[rg[c]] + rank] = cur.first + c * INGEST_THREADS + tid;
+    for (int c = 0; c < CHUNKS; c++) {
+      const uint32_t i = first + c * 32 + lane;
+      const bool valid = ring[c] != 0xFFFFFFFFu;
+      // 32 consecutive points of a spinning sensor carry 32 different ring ids: every lane writes its number into
+      // its ring's probe slot and finds it again unless another lane has the same ring. Then the stable rank needs
+      // no comparison of all lanes with all lanes (match.any, which is slowest exactly when all ids differ).
+      if (valid) { probe[ring[c]] = (uint8_t)lane; }
+      __syncwarp();
+      const bool alone = !valid || probe[ring[c]] == (uint8_t)lane;
+      uint32_t lpos = 0;
+      if (__all_sync(0xFFFFFFFFu, alone)) {
+        if (valid) {
+          const uint32_t base = my[ring[c]];
+          my[ring[c]] = base + 1u;
+          lpos = toff[ring[c]] + base;
+        }
+      } else {
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, ring[c]);
+        if (valid) {
+          const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+          const uint32_t base = my[ring[c]];
+          __syncwarp(peers);
+          if (rank == 0) { my[ring[c]] = base + __popc(peers); }
+          lpos = toff[ring[c]] + base + rank;
+        }
       }
+      if (valid) { s_out[lpos] = i; s_ring[lpos] = (uint16_t)ring[c]; }
+      __syncwarp();
+    }
+    __syncthreads();
+    // the tile's points, now grouped by ring in stable order, go out run by run: consecutive threads write consecutive
+    // words of a ring's bucket (whole 32-byte sectors instead of 2048 scattered 4-byte stores)
+    for (uint32_t e = threadIdx.x; e < s_total; e += blockDim.x) {
+      const uint32_t r = s_ring[e];
+      idx[cur.point_base + gbase[r] + (e - toff[r])] = s_out[e];
     }
     cur = nxt;
   }

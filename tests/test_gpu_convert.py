@@ -202,6 +202,19 @@ def test_device_resident_input_and_chaining_into_the_extraction():
         out = fe.fetch()
         compare_scan(out, 0, want_cloud, want)
         compare_scan(out, 1, want_cloud, want)
+        # the bulk form of the same chain (one marshalled batch, one call for all views): the bucketing then reads the
+        # converter's ring-id by-product instead of the points, and a failed cloud in the middle is left out
+        bad = PointCloud2(data=d_raw, point_step=48, fields=[PointField(f.name, f.offset, f.datatype) for f in fields[:5]])  # no ring
+        batch = conv.marshal([msg, bad, msg])
+        for _ in range(2):
+            conv.convert_batch(batch)
+            views = conv.views()
+            assert views.n_views == 2 and conv.status_of(1) != 0
+            fe.extract_views(views)
+            out = fe.fetch()
+            assert fe.batch_stats()["general_scans"] == 2
+            compare_scan(out, 0, want_cloud, want)
+            compare_scan(out, 1, want_cloud, want)
 
 
 def test_common_plan_fast_kernel_special_values(conv):
