@@ -183,10 +183,10 @@ k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t 
   }
   if (tid == 0) { gen_tile_base[carry_c] = carry_t; counters[C_GEN_SCANS] = carry_c; counters[C_GEN_TILES] = carry_t; }
   __syncthreads();
-  // general tile -> its entry of gen_scan, one flagged scan after the other with the whole CTA on its tiles (coalesced)
-  for (uint32_t k = 0; k < carry_c; k++) {
+  // general tile -> its entry of gen_scan: one warp per flagged scan, lanes on consecutive tiles (coalesced)
+  for (uint32_t k = (uint32_t)tid >> 5; k < carry_c; k += 32) {
     const uint32_t tb = gen_tile_base[k], te = gen_tile_base[k + 1];
-    for (uint32_t j = tb + tid; j < te; j += 1024) { tile_owner[j] = k; }
+    for (uint32_t j = tb + (tid & 31); j < te; j += 32) { tile_owner[j] = k; }
   }
 }
 
@@ -337,19 +337,33 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
   uint16_t * s_ring = reinterpret_cast<uint16_t *>(s_out + TILE);
   uint8_t * probe = reinterpret_cast<uint8_t *>(s_ring + TILE) + warp * R;
   __shared__ uint32_t s_total;
-  TileJob cur = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, t);
-  for (; t < n_tiles; t += gridDim.x) {
-    // the next tile's descriptor chain (three dependent loads) runs while this tile is processed
-    const uint32_t tn = t + gridDim.x < n_tiles ? t + gridDim.x : t;
-    const TileJob nxt = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, tn);
-    const uint16_t * src16 = cur.src16 ? cur.src16 : ring16 + cur.point_base;   // converter by-product, else k_ring_hist's copy
-    const uint32_t first = cur.first + warp * PER_WARP;
-    uint32_t ring[CHUNKS];
+  // software pipeline over the CTA's tiles: the descriptor chain (three dependent loads) is fetched two tiles ahead,
+  // the ring ids and (for up to 256 rings) the bucket bases one tile ahead, so that none of these latencies is paid
+  // between the barriers of a tile
+  auto load_ids = [&](const TileJob & j, uint32_t (&ring)[CHUNKS]) {
+    const uint16_t * src16 = j.src16 ? j.src16 : ring16 + j.point_base;   // converter by-product, else k_ring_hist's copy
+    const uint32_t first = j.first + warp * PER_WARP;
 #pragma unroll
     for (int c = 0; c < CHUNKS; c++) {
       const uint32_t i = first + c * 32 + lane;
-      ring[c] = i < cur.n_points ? (uint32_t)src16[i] : 0xFFFFFFFFu;
+      ring[c] = i < j.n_points ? (uint32_t)src16[i] : 0xFFFFFFFFu;
     }
+  };
+  auto load_base = [&](const TileJob & j) -> uint32_t {
+    const int r = threadIdx.x;
+    return r < R ? rings[(size_t)j.scan * R + r].offset + tile_hist[(size_t)j.tile * R + r] : 0u;
+  };
+  auto clamp_t = [&](uint32_t u) { return u < n_tiles ? u : n_tiles - 1; };
+  TileJob cur = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, t);
+  TileJob nxt = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, clamp_t(t + gridDim.x));
+  uint32_t ring[CHUNKS], ring_n[CHUNKS];
+  load_ids(cur, ring);
+  uint32_t base0 = load_base(cur);
+  for (; t < n_tiles; t += gridDim.x) {
+    const TileJob nxt2 = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, clamp_t(t + 2 * gridDim.x));
+    load_ids(nxt, ring_n);
+    const uint32_t base0_n = load_base(nxt);
+    const uint32_t first = cur.first + warp * PER_WARP;
     __syncthreads();   // the previous tile's arrays are no longer used
     for (int r = threadIdx.x; r < WARPS * R; r += blockDim.x) { s_base[r] = 0; }
     __syncthreads();
@@ -369,7 +383,7 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
         run += c;
       }
       tcount[r] = run;
-      gbase[r] = run ? rings[(size_t)cur.scan * R + r].offset + tile_hist[(size_t)cur.tile * R + r] : 0u;
+      gbase[r] = r == (int)threadIdx.x ? base0 : rings[(size_t)cur.scan * R + r].offset + tile_hist[(size_t)cur.tile * R + r];
     }
     __syncthreads();
     if (warp == 0) {   // exclusive prefix of the run lengths over the rings: the runs' places in the staging array
@@ -422,7 +436,9 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
       const uint32_t r = s_ring[e];
       idx[cur.point_base + gbase[r] + (e - toff[r])] = s_out[e];
     }
-    cur = nxt;
+    cur = nxt; nxt = nxt2; base0 = base0_n;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; c++) { ring[c] = ring_n[c]; }
   }
 }
 
