@@ -172,7 +172,7 @@ def workload_config(workload: str, sensor: str, rings: int, cols: int, scans_per
     same-config check compares like with like."""
     return {"workload": workload, "sensor": sensor, "rings": rings, "cols": cols, "scans_per_gpu": scans_per_gpu,
             "points_per_gpu": points_per_gpu, "params": PARAMS_NOTE,
-            "sharding": "frames by index, no data-path collective; NCCL all-gather of per-scan counts" if world > 1 else "single GPU",
+            "sharding": "frames by index, no data-path collective; per-scan counts exchanged between the ranks (lfx_shard_*)" if world > 1 else "single GPU",
             "l2": f"inputs {points_per_gpu * 32 / 1e9:.2f} GB per GPU, larger than the 126 MB L2 (no flush needed)"}
 
 
@@ -520,8 +520,20 @@ def main():
         [FeatureExtraction.wire_view((d_in.data_ptr() + int(offs[s]) * 32, sizes[s])) for s in range(scans_per_gpu)])
     # the path's only exchange: all-gather of per-scan (n_edge, n_surface) over NVLink on a side stream (it overlaps
     # the next batch); global offsets follow from a local exclusive scan. join() puts it back on the timed stream.
-    gather_mode = os.environ.get("LFX_BENCH_GATHER", "sync")   # diagnosis only: sync (default) | overlap | none
-    sharded = sharding.ShardedExtraction(fe, n_frames, dev, overlap=(gather_mode == "overlap"))
+    # The path's only exchange: every rank's per-scan (n_edge, n_surface) reach every rank, global offsets follow from a
+    # scan. Default: the library's own driver (lfx_shard_*: NCCL set-up, counts pushed through peer-mapped memory over
+    # NVLink by a one-CTA kernel at the tail of the batch). Diagnosis: LFX_BENCH_GATHER=torch (all_gather_into_tensor
+    # on the extraction stream) | overlap (the same on a side stream) | none.
+    gather_mode = os.environ.get("LFX_BENCH_GATHER", "abi") if world > 1 else "none"
+    if gather_mode == "none":
+        class _NoExchange:      # a single GPU has nobody to tell
+            def join(self):
+                pass
+        sharded = _NoExchange()
+    elif gather_mode == "abi":
+        sharded = sharding.AbiShard(fe, n_frames, rank, world)
+    else:
+        sharded = sharding.ShardedExtraction(fe, n_frames, dev, overlap=(gather_mode == "overlap"))
 
     def step_device():
         if gather_mode == "none":
@@ -573,7 +585,29 @@ def main():
 
     # ---- the exchange alone (N > 1): device time from the end of the batch to the end of the all-gather
     exchange = None
-    if world > 1 and gather_mode == "sync":
+    if world > 1 and gather_mode == "abi":
+        # device time of what the exchange adds to a step on the extraction stream: the scan of the previous exchange
+        # (its peers' flags arrived a batch ago) + the push of this one
+        evs = []
+        for _ in range(6):
+            fe.extract_views(dev_views, keep=d_in)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            sharded.exchange()
+            b.record(stream)
+            evs.append((a, b))
+        sharded.join()
+        torch.cuda.synchronize()
+        g = [a.elapsed_time(b) for a, b in evs][1:]
+        t = torch.tensor([float(np.mean(g)), float(np.max(g))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        counts_all, offsets_all = sharded.fetch()
+        info = sharded.info()
+        exchange = {"ms_mean": float(t[0].item()), "ms_max": float(t[1].item()), "bytes_per_rank": 8 * scans_per_gpu,
+                    "mechanism": info["exchange"], "nccl_ranks": info["nccl_ranks"], "frames_in_global_table": int(counts_all.shape[0]),
+                    "global_features": [int(offsets_all[-1, 0]), int(offsets_all[-1, 1])],
+                    "how": "CUDA events around lfx_shard_exchange on the extraction stream (scan of the previous exchange + push of this one), max over ranks"}
+    elif world > 1 and gather_mode == "torch":
         sharded.time_gather = True
         for _ in range(6):
             step_device()
@@ -581,7 +615,7 @@ def main():
         sharded.time_gather = False
         t = torch.tensor([float(np.mean(g)), float(np.max(g))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        exchange = {"all_gather_ms_mean": float(t[0].item()), "all_gather_ms_max": float(t[1].item()),
+        exchange = {"ms_mean": float(t[0].item()), "ms_max": float(t[1].item()), "mechanism": "torch.distributed all_gather_into_tensor (NCCL)",
                     "bytes_per_rank": 8 * scans_per_gpu, "how": "CUDA events around the collective on the extraction stream, max over ranks"}
 
     # ---- dominant kernel (k_extract_sectors) timed live with CUDA events on the launching stream
@@ -642,7 +676,9 @@ def main():
 
         def step_e2e():
             res = fe.extract_views(host_views)
-            if world > 1:
+            if world > 1 and gather_mode == "abi":
+                sharded.exchange()
+            elif world > 1:
                 sharding.gather_counts(sharding.device_counts_tensor(res, dev), n_frames)
             rc = lib.lfx_fetch_counts(fe.handle, h_counts.ctypes.data, h_offsets.ctypes.data)
             rc |= lib.lfx_fetch_features(fe.handle, h_edge, 2 * max(n_feat, 1), h_surf, 2 * max(n_feat, 1))

@@ -400,6 +400,46 @@ int lfx_synth_scan_host(const lfx_synth_spec *spec, uint64_t frame, void *out, u
 int lfx_synth_batch_device(lfx_handle *h, const lfx_synth_spec *spec, uint64_t first_frame, int n_scans,
                            void *d_out);
 
+/* ------------------------------------------------------------------ multi-GPU driver (SURVEY.md 8(b) "Threading", 8(e))
+ * Scans are independent (the reference's callback is const and stateless, feature_extraction.cpp:92,173-175): a
+ * sequence of n_frames scans is sharded by frame index, rank g of G owning frames [g F / G, (g + 1) F / G) on its own
+ * GPU and handle. No point or feature crosses GPUs; the one exchange is that every rank's per-scan counts
+ * (n_edge, n_surface) reach every rank, which derives where each frame's clouds start in the frame-ordered
+ * concatenation. One lfx_shard per rank, either one process per GPU (lfx_shard_create; NCCL rendezvous through a
+ * unique id) or all ranks in one process (lfx_shard_create_local). NCCL (loaded at run time) sets the group up; the
+ * per-batch exchange itself is a one-CTA kernel that stores the counts into every peer's receive buffer through
+ * peer-mapped memory over NVLink and raises a flag, so no collective kernel has to wait for SMs behind the persistent
+ * extraction kernel (set LFX_SHARD_EXCHANGE=nccl to use ncclAllGather instead; it is also the fallback when the
+ * buffers cannot be peer-mapped).
+ *
+ * Per batch:  lfx_extract_batch(h, this rank's scans) ; lfx_shard_exchange(s) ;  ... next batch ...
+ * and lfx_shard_finish / lfx_shard_fetch whenever the global tables are needed (the consumer side of an exchange is
+ * enqueued lazily: at the next exchange, or here). Everything is enqueued on the handle's stream. */
+#define LFX_SHARD_ID_BYTES 128
+typedef struct lfx_shard lfx_shard;
+typedef struct lfx_shard_result {
+  uint64_t n_frames;
+  uint64_t first_frame, last_frame;  /* this rank's shard [first, last) */
+  const uint32_t *d_counts_all;      /* [n_frames][2] (n_edge, n_surface) in frame order, on this rank's device */
+  const uint64_t *d_offsets_all;     /* [n_frames + 1][2] exclusive prefix (last row = totals) */
+} lfx_shard_result;
+int lfx_shard_range(uint64_t n_frames, int rank, int world, uint64_t *first, uint64_t *last);
+/* rank 0: LFX_SHARD_ID_BYTES bytes to hand to every rank by whatever means the host program has (ncclGetUniqueId) */
+int lfx_shard_unique_id(void *id_out);
+/* one process (or thread) per rank; blocks until all `world` ranks have called it (ncclCommInitRank) */
+int lfx_shard_create(lfx_handle *h, const void *unique_id, int rank, int world, uint64_t n_frames, lfx_shard **out);
+/* all ranks in the calling process: handles[world] on distinct devices -> out[world] (ncclCommInitAll) */
+int lfx_shard_create_local(lfx_handle **handles, int world, uint64_t n_frames, lfx_shard **out);
+/* publish the counts of the handle's last batch (which must be this rank's shard) to every rank; asynchronous */
+int lfx_shard_exchange(lfx_shard *s);
+/* global tables of the last exchange, valid once the handle's stream has reached this point (lfx_synchronize) */
+int lfx_shard_finish(lfx_shard *s, lfx_shard_result *out);
+/* the same, copied to the host (either pointer may be NULL); synchronises; LFX_E_STATE if a peer never published */
+int lfx_shard_fetch(lfx_shard *s, uint32_t *counts_all /* [n_frames][2] */, uint64_t *offsets_all /* [n_frames+1][2] */);
+int lfx_shard_info(const lfx_shard *s, int *uses_peer_stores, int *nccl_ranks);
+const char *lfx_shard_last_error(const lfx_shard *s);
+void lfx_shard_destroy(lfx_shard *s);
+
 #ifdef __cplusplus
 }
 #endif

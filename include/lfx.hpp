@@ -222,5 +222,62 @@ private:
   lfx_handle * h_;
 };
 
+// One rank of the multi-GPU driver ("multi-GPU driver owns 8 handles + NCCL comm"; 8(e)): frames are
+// sharded by index, rank g of G owning [g F / G, (g + 1) F / G). Per batch: fe.ExtractBatch(this rank's scans), then
+// Exchange(); Fetch() (or Finish() for the device-side tables) whenever the frame-ordered global tables are needed.
+class Shard
+{
+public:
+  // one process (or thread) per rank: `unique_id` = the bytes rank 0 got from UniqueId()
+  Shard(FeatureExtraction & fe, const std::vector<uint8_t> & unique_id, int rank, int world, uint64_t n_frames)
+  {
+    const int rc = lfx_shard_create(fe.handle(), unique_id.empty() ? nullptr : unique_id.data(), rank, world, n_frames, &s_);
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(fe.handle())); }
+  }
+  static std::vector<uint8_t> UniqueId()
+  {
+    std::vector<uint8_t> id(LFX_SHARD_ID_BYTES);
+    const int rc = lfx_shard_unique_id(id.data());
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(nullptr)); }
+    return id;
+  }
+  // all ranks in this process: one Shard per FeatureExtraction (distinct devices), rank = position
+  static std::vector<Shard> Local(const std::vector<FeatureExtraction *> & fes, uint64_t n_frames)
+  {
+    std::vector<lfx_handle *> hs;
+    for (FeatureExtraction * fe : fes) { hs.push_back(fe->handle()); }
+    std::vector<lfx_shard *> out(fes.size(), nullptr);
+    const int rc = lfx_shard_create_local(hs.data(), static_cast<int>(hs.size()), n_frames, out.data());
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(hs.empty() ? nullptr : hs[0])); }
+    std::vector<Shard> shards;
+    for (lfx_shard * s : out) { shards.push_back(Shard(s)); }
+    return shards;
+  }
+  Shard(Shard && o) noexcept : s_(o.s_) { o.s_ = nullptr; }
+  Shard(const Shard &) = delete;
+  Shard & operator=(const Shard &) = delete;
+  ~Shard() { lfx_shard_destroy(s_); }
+
+  static void Range(uint64_t n_frames, int rank, int world, uint64_t & first, uint64_t & last)
+  {
+    if (lfx_shard_range(n_frames, rank, world, &first, &last) != LFX_OK) { throw Error(LFX_E_BAD_PARAM, "rank outside the world"); }
+  }
+  void Exchange() { Check(lfx_shard_exchange(s_)); }
+  lfx_shard_result Finish() { lfx_shard_result r; Check(lfx_shard_finish(s_, &r)); return r; }
+  // counts [n_frames][2] and offsets [n_frames + 1][2] of the last exchange, in frame order (synchronises)
+  void Fetch(std::vector<uint32_t> & counts, std::vector<uint64_t> & offsets, uint64_t n_frames)
+  {
+    counts.resize(2 * n_frames);
+    offsets.resize(2 * (n_frames + 1));
+    Check(lfx_shard_fetch(s_, counts.data(), offsets.data()));
+  }
+  bool UsesPeerStores() const { int p = 0; lfx_shard_info(s_, &p, nullptr); return p != 0; }
+
+private:
+  explicit Shard(lfx_shard * s) : s_(s) {}
+  void Check(int rc) { if (rc != LFX_OK) { throw Error(rc, lfx_shard_last_error(s_)); } }
+  lfx_shard * s_ = nullptr;
+};
+
 }  // namespace lfx
 #endif  // LFX_HPP_

@@ -114,6 +114,16 @@ class ScanOutput(C.Structure):
     ]
 
 
+class ShardResult(C.Structure):
+    """lfx_shard_result."""
+
+    _fields_ = [("n_frames", C.c_uint64), ("first_frame", C.c_uint64), ("last_frame", C.c_uint64),
+                ("d_counts_all", C.c_void_p), ("d_offsets_all", C.c_void_p)]
+
+
+SHARD_ID_BYTES = 128
+
+
 class BatchStats(C.Structure):
     _fields_ = [("fast_rings", C.c_uint32 * 3), ("general_scans", C.c_uint32), ("general_rings", C.c_uint32),
                 ("indexed_rings", C.c_uint32 * 3)]
@@ -244,5 +254,18 @@ def lib() -> C.CDLL:
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]
     L.lfx_synth_scan_host.argtypes = [C.POINTER(SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
     L.lfx_synth_batch_device.argtypes = [H, C.POINTER(SynthSpec), C.c_uint64, C.c_int, C.c_void_p]
+    S = C.c_void_p
+    L.lfx_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.lfx_shard_unique_id.argtypes = [C.c_void_p]
+    L.lfx_shard_create.argtypes = [H, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.POINTER(S)]
+    L.lfx_shard_create_local.argtypes = [C.POINTER(H), C.c_int, C.c_uint64, C.POINTER(S)]
+    L.lfx_shard_exchange.argtypes = [S]
+    L.lfx_shard_finish.argtypes = [S, C.POINTER(ShardResult)]
+    L.lfx_shard_fetch.argtypes = [S, C.c_void_p, C.c_void_p]
+    L.lfx_shard_info.argtypes = [S, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.lfx_shard_last_error.argtypes = [S]
+    L.lfx_shard_last_error.restype = C.c_char_p
+    L.lfx_shard_destroy.argtypes = [S]
+    L.lfx_shard_destroy.restype = None
     _lib = L
     return L

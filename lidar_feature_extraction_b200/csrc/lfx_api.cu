@@ -25,6 +25,11 @@
 #include "lfx_convert.cuh"
 #include "lfx_color.cuh"
 #include "lfx_map.cuh"
+#include "lfx_shard.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>      // types only: the library is loaded at run time (lfx_shard_*), single-GPU users do not need it
+#include <unistd.h>
 
 using namespace lfxk;
 
@@ -1607,6 +1612,378 @@ int lfx_map_clear(lfx_handle * h)
   h->map_points = 0;
   h->map_empty = true;
   return LFX_OK;
+}
+
+}  // extern "C"
+
+// ====================================================================== multi-GPU driver
+
+namespace
+{
+
+// NCCL is loaded at run time: the same libnccl.so.2 a host program (or torch) has already mapped is found first.
+struct NcclApi
+{
+  void * lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int *) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char * (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+};
+
+NcclApi * nccl_api()
+{
+  static NcclApi api;
+  if (api.lib || !api.err.empty()) { return &api; }
+  for (const char * name : {"libnccl.so.2", "libnccl.so"}) {
+    api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) { break; }
+  }
+  if (!api.lib) { api.err = "libnccl.so.2 could not be loaded (the multi-GPU driver needs NCCL)"; return &api; }
+  auto sym = [&](const char * n) { void * p = dlsym(api.lib, n); if (!p && api.err.empty()) { api.err = std::string("NCCL lacks ") + n; } return p; };
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+  api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+  api.CommCount = reinterpret_cast<decltype(api.CommCount)>(sym("ncclCommCount"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  return &api;
+}
+
+struct ShardWire   // what every rank tells every other rank at set-up
+{
+  cudaIpcMemHandle_t ipc;
+  uint64_t pid;
+  uint64_t ptr;       // the receive buffer's address in the owner's process (used when pid matches)
+  int32_t device;
+  int32_t pad;
+};
+
+}  // namespace
+
+struct lfx_shard
+{
+  lfx_handle * h = nullptr;
+  int rank = 0, world = 1;
+  uint64_t n_frames = 0, first = 0, last = 0;
+  uint32_t width = 0;             // rows of a block: the largest shard
+  ncclComm_t comm = nullptr;
+  int nranks = 0;
+  bool p2p = false;
+  uint32_t * d_recv = nullptr;    // two receive slots (parity of the epoch)
+  size_t slot_words = 0;
+  uint32_t * peer_recv[lfxk::SHARD_MAX_WORLD] = {nullptr};   // peers' d_recv as mapped into this process
+  bool peer_opened[lfxk::SHARD_MAX_WORLD] = {false};
+  uint32_t * d_send = nullptr;    // NCCL mode: this rank's block, zero padded to width rows
+  uint32_t * d_counts_all = nullptr;
+  unsigned long long * d_offsets_all = nullptr;
+  uint32_t * d_status = nullptr;
+  uint32_t epoch = 0;             // exchanges started
+  uint32_t finished = 0;          // exchanges whose scan has been enqueued
+  std::string err;
+};
+
+namespace
+{
+
+int shard_fail(lfx_shard * s, int code, const std::string & msg) { s->err = msg; if (s->h) { s->h->err = msg; } return code; }
+
+#define LFX_SHARD_CUDA(s, call)                                                                    \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) { return shard_fail(s, LFX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); } \
+  } while (0)
+#define LFX_SHARD_NCCL(s, call)                                                                    \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess) { return shard_fail(s, LFX_E_CUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(r__)); } \
+  } while (0)
+
+// buffers + peer mapping, after s->comm exists. `wires`: null = gather them with NCCL (one process per rank)
+int shard_setup(lfx_shard * s, const ShardWire * local_wires)
+{
+  NcclApi * nc = nccl_api();
+  lfx_handle * h = s->h;
+  LFX_SHARD_CUDA(s, cudaSetDevice(h->device));
+  s->width = 0;
+  for (int g = 0; g < s->world; g++) {
+    const uint64_t a = ((uint64_t)g * s->n_frames) / (uint64_t)s->world, b = ((uint64_t)(g + 1) * s->n_frames) / (uint64_t)s->world;
+    s->width = std::max<uint32_t>(s->width, (uint32_t)(b - a));
+  }
+  s->slot_words = lfxk::shard_slot_words(s->world, s->width);
+  if (!local_wires) {   // (single-process groups allocate before they call this)
+    LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_recv), sizeof(uint32_t) * 2 * s->slot_words));
+    LFX_SHARD_CUDA(s, cudaMemset(s->d_recv, 0, sizeof(uint32_t) * 2 * s->slot_words));
+  }
+  LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_send), sizeof(uint32_t) * 2 * std::max<uint32_t>(s->width, 1)));
+  LFX_SHARD_CUDA(s, cudaMemset(s->d_send, 0, sizeof(uint32_t) * 2 * std::max<uint32_t>(s->width, 1)));
+  LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_counts_all), sizeof(uint32_t) * 2 * std::max<uint64_t>(s->n_frames, 1)));
+  LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_offsets_all), sizeof(unsigned long long) * 2 * (s->n_frames + 1)));
+  LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_status), sizeof(uint32_t)));
+  LFX_SHARD_CUDA(s, cudaMemset(s->d_status, 0, sizeof(uint32_t)));
+  LFX_SHARD_NCCL(s, nc->CommCount(s->comm, &s->nranks));
+  // (a group inside one process always pushes: one host thread cannot issue a rank's ncclAllGather without the
+  // other ranks' calls in the same NCCL group, which a per-rank entry point cannot provide)
+  const char * mode = getenv("LFX_SHARD_EXCHANGE");
+  const bool want_p2p = (local_wires || !(mode && strcmp(mode, "nccl") == 0)) && s->world <= lfxk::SHARD_MAX_WORLD;
+  std::vector<ShardWire> wires((size_t)s->world);
+  if (local_wires) {
+    memcpy(wires.data(), local_wires, sizeof(ShardWire) * (size_t)s->world);
+  } else {
+    ShardWire mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.pid = (uint64_t)getpid();
+    mine.ptr = reinterpret_cast<uint64_t>(s->d_recv);
+    mine.device = h->device;
+    const bool ipc_ok = cudaIpcGetMemHandle(&mine.ipc, s->d_recv) == cudaSuccess;
+    if (!ipc_ok) { cudaGetLastError(); mine.pid = 0; }   // pid 0: "cannot be mapped"
+    ShardWire * d_w = nullptr;
+    LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&d_w), sizeof(ShardWire) * ((size_t)s->world + 1)));
+    LFX_SHARD_CUDA(s, cudaMemcpyAsync(d_w + s->world, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->stream));
+    LFX_SHARD_NCCL(s, nc->AllGather(d_w + s->world, d_w, sizeof(ShardWire), ncclChar, s->comm, h->stream));
+    LFX_SHARD_CUDA(s, cudaMemcpyAsync(wires.data(), d_w, sizeof(ShardWire) * (size_t)s->world, cudaMemcpyDeviceToHost, h->stream));
+    LFX_SHARD_CUDA(s, cudaStreamSynchronize(h->stream));
+    cudaFree(d_w);
+  }
+  bool ok = want_p2p;
+  for (int p = 0; p < s->world && ok; p++) {
+    const ShardWire & w = wires[(size_t)p];
+    if (p == s->rank) { s->peer_recv[p] = s->d_recv; continue; }
+    if (w.pid == 0) { ok = false; break; }
+    if (w.pid == (uint64_t)getpid()) {   // same process: plain peer access
+      int can = 0;
+      if (w.device != h->device) {
+        if (cudaDeviceCanAccessPeer(&can, h->device, w.device) != cudaSuccess || !can) { cudaGetLastError(); ok = false; break; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(w.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = false; break; }
+        cudaGetLastError();
+      }
+      s->peer_recv[p] = reinterpret_cast<uint32_t *>(w.ptr);
+    } else {
+      void * q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, w.ipc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      s->peer_recv[p] = static_cast<uint32_t *>(q);
+      s->peer_opened[p] = true;
+    }
+  }
+  // every rank must take the same path: agree through one more (tiny) all-gather, which is also the barrier after
+  // which no rank's receive buffer is being zeroed any more
+  if (!local_wires) {
+    uint32_t * d_v = nullptr;
+    LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&d_v), sizeof(uint32_t) * ((size_t)s->world + 1)));
+    const uint32_t v = ok ? 1u : 0u;
+    LFX_SHARD_CUDA(s, cudaMemcpyAsync(d_v + s->world, &v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+    LFX_SHARD_NCCL(s, nc->AllGather(d_v + s->world, d_v, 1, ncclUint32, s->comm, h->stream));
+    std::vector<uint32_t> votes((size_t)s->world);
+    LFX_SHARD_CUDA(s, cudaMemcpyAsync(votes.data(), d_v, sizeof(uint32_t) * (size_t)s->world, cudaMemcpyDeviceToHost, h->stream));
+    LFX_SHARD_CUDA(s, cudaStreamSynchronize(h->stream));
+    cudaFree(d_v);
+    for (uint32_t x : votes) { ok = ok && x != 0; }
+  }
+  s->p2p = ok;
+  return LFX_OK;
+}
+
+lfxk::ShardScanArgs shard_scan_args(lfx_shard * s)
+{
+  lfxk::ShardScanArgs a;
+  a.slot = s->d_recv + (size_t)(s->epoch & 1u) * s->slot_words;
+  a.counts_all = s->d_counts_all;
+  a.offsets_all = s->d_offsets_all;
+  a.status = s->d_status;
+  a.n_frames = s->n_frames;
+  a.world = s->world;
+  a.width = s->width;
+  a.epoch = s->p2p ? s->epoch : 0u;
+  a.timeout_ns = 10ull * 1000 * 1000 * 1000;   // a peer that is 10 s late is gone: report instead of hanging the GPU
+  return a;
+}
+
+int shard_enqueue_scan(lfx_shard * s)
+{
+  lfx_handle * h = s->h;
+  lfxk::k_shard_scan<<<1, lfxk::SHARD_THREADS, 0, h->stream>>>(shard_scan_args(s));
+  LFX_SHARD_CUDA(s, cudaGetLastError());
+  h->launches += 1;
+  s->finished = s->epoch;
+  return LFX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lfx_shard_range(uint64_t n_frames, int rank, int world, uint64_t * first, uint64_t * last)
+{
+  if (world <= 0 || rank < 0 || rank >= world || !first || !last) { return LFX_E_BAD_PARAM; }
+  *first = ((uint64_t)rank * n_frames) / (uint64_t)world;
+  *last = ((uint64_t)(rank + 1) * n_frames) / (uint64_t)world;
+  return LFX_OK;
+}
+
+int lfx_shard_unique_id(void * id_out)
+{
+  if (!id_out) { return LFX_E_BAD_PARAM; }
+  NcclApi * nc = nccl_api();
+  if (!nc->err.empty()) { g_create_error = nc->err; return LFX_E_STATE; }
+  static_assert(sizeof(ncclUniqueId) <= LFX_SHARD_ID_BYTES, "unique id fits the ABI's byte array");
+  ncclUniqueId id;
+  const ncclResult_t r = nc->GetUniqueId(&id);
+  if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + nc->GetErrorString(r); return LFX_E_CUDA; }
+  memset(id_out, 0, LFX_SHARD_ID_BYTES);
+  memcpy(id_out, &id, sizeof(id));
+  return LFX_OK;
+}
+
+int lfx_shard_create(lfx_handle * h, const void * unique_id, int rank, int world, uint64_t n_frames, lfx_shard ** out)
+{
+  if (!h || !out || world <= 0 || rank < 0 || rank >= world || (world > 1 && !unique_id)) { return LFX_E_BAD_PARAM; }
+  NcclApi * nc = nccl_api();
+  if (!nc->err.empty()) { return fail(h, LFX_E_STATE, nc->err); }
+  lfx_shard * s = new lfx_shard();
+  s->h = h; s->rank = rank; s->world = world; s->n_frames = n_frames;
+  lfx_shard_range(n_frames, rank, world, &s->first, &s->last);
+  if (cudaSetDevice(h->device) != cudaSuccess) { delete s; return fail(h, LFX_E_CUDA, "cudaSetDevice"); }
+  ncclUniqueId id;
+  if (world > 1) { memcpy(&id, unique_id, sizeof(id)); }
+  else if (nc->GetUniqueId(&id) != ncclSuccess) { delete s; return fail(h, LFX_E_CUDA, "ncclGetUniqueId"); }
+  const ncclResult_t r = nc->CommInitRank(&s->comm, world, id, rank);
+  if (r != ncclSuccess) { const std::string m = std::string("ncclCommInitRank: ") + nc->GetErrorString(r); delete s; return fail(h, LFX_E_CUDA, m); }
+  const int rc = shard_setup(s, nullptr);
+  if (rc != LFX_OK) { lfx_shard_destroy(s); return rc; }
+  *out = s;
+  return LFX_OK;
+}
+
+int lfx_shard_create_local(lfx_handle ** handles, int world, uint64_t n_frames, lfx_shard ** out)
+{
+  if (!handles || !out || world <= 0 || world > lfxk::SHARD_MAX_WORLD) { return LFX_E_BAD_PARAM; }
+  NcclApi * nc = nccl_api();
+  if (!nc->err.empty()) { return fail(handles[0], LFX_E_STATE, nc->err); }
+  std::vector<int> devs((size_t)world);
+  for (int g = 0; g < world; g++) { if (!handles[g]) { return LFX_E_BAD_PARAM; } devs[(size_t)g] = handles[g]->device; }
+  std::vector<ncclComm_t> comms((size_t)world, nullptr);
+  const ncclResult_t r = nc->CommInitAll(comms.data(), world, devs.data());
+  if (r != ncclSuccess) { return fail(handles[0], LFX_E_CUDA, std::string("ncclCommInitAll: ") + nc->GetErrorString(r)); }
+  std::vector<ShardWire> wires((size_t)world);
+  std::vector<lfx_shard *> made;
+  int rc = LFX_OK;
+  for (int g = 0; g < world; g++) {
+    lfx_shard * s = new lfx_shard();
+    made.push_back(s);
+    s->h = handles[g]; s->rank = g; s->world = world; s->n_frames = n_frames; s->comm = comms[(size_t)g];
+    lfx_shard_range(n_frames, g, world, &s->first, &s->last);
+    uint32_t width = 0;
+    for (int k = 0; k < world; k++) { uint64_t a, b; lfx_shard_range(n_frames, k, world, &a, &b); width = std::max<uint32_t>(width, (uint32_t)(b - a)); }
+    const size_t words = lfxk::shard_slot_words(world, width);
+    if (cudaSetDevice(s->h->device) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&s->d_recv), sizeof(uint32_t) * 2 * words) != cudaSuccess ||
+        cudaMemset(s->d_recv, 0, sizeof(uint32_t) * 2 * words) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+      rc = fail(handles[0], LFX_E_CUDA, "receive buffer allocation failed");
+      break;
+    }
+    memset(&wires[(size_t)g], 0, sizeof(ShardWire));
+    wires[(size_t)g].pid = (uint64_t)getpid();
+    wires[(size_t)g].ptr = reinterpret_cast<uint64_t>(s->d_recv);
+    wires[(size_t)g].device = s->h->device;
+  }
+  bool all_p2p = true;
+  for (int g = 0; g < world && rc == LFX_OK; g++) {
+    rc = shard_setup(made[(size_t)g], wires.data());
+    all_p2p = all_p2p && made[(size_t)g]->p2p;
+  }
+  if (rc == LFX_OK && !all_p2p) { rc = fail(handles[0], LFX_E_STATE, "the GPUs of a single-process group must be able to map each other's memory (peer access)"); }
+  if (rc != LFX_OK) { for (lfx_shard * s : made) { lfx_shard_destroy(s); } return rc; }
+  for (int g = 0; g < world; g++) { out[g] = made[(size_t)g]; }
+  return LFX_OK;
+}
+
+int lfx_shard_exchange(lfx_shard * s)
+{
+  if (!s) { return LFX_E_BAD_PARAM; }
+  lfx_handle * h = s->h;
+  if (!h->have_batch) { return shard_fail(s, LFX_E_STATE, "no batch has been extracted"); }
+  if ((uint64_t)h->n_scans != s->last - s->first) { return shard_fail(s, LFX_E_BAD_PARAM, "the last batch is not this rank's shard"); }
+  LFX_SHARD_CUDA(s, cudaSetDevice(h->device));
+  // the scan of the previous exchange goes first: after it this rank no longer reads the slot its peers write next
+  const uint32_t n_local = (uint32_t)h->n_scans;
+  if (s->p2p) {
+    const bool scan_first = s->finished != s->epoch;
+    const lfxk::ShardScanArgs sa = shard_scan_args(s);   // (of the previous epoch)
+    s->epoch += 1;
+    lfxk::ShardPushArgs pa;
+    pa.counts = h->d_counts.p; pa.n_local = n_local; pa.rank = s->rank; pa.world = s->world; pa.width = s->width; pa.epoch = s->epoch;
+    for (int p = 0; p < s->world; p++) { pa.peers.slot[p] = s->peer_recv[p] + (size_t)(s->epoch & 1u) * s->slot_words; }
+    if (scan_first) { lfxk::k_shard_scan_push<<<1, lfxk::SHARD_THREADS, 0, h->stream>>>(sa, pa); s->finished = s->epoch - 1; }
+    else { lfxk::k_shard_push<<<1, lfxk::SHARD_THREADS, 0, h->stream>>>(pa); }
+    LFX_SHARD_CUDA(s, cudaGetLastError());
+    h->launches += 1;
+  } else {
+    if (s->finished != s->epoch) { const int rc = shard_enqueue_scan(s); if (rc != LFX_OK) { return rc; } }
+    s->epoch += 1;
+    NcclApi * nc = nccl_api();
+    LFX_SHARD_CUDA(s, cudaMemcpyAsync(s->d_send, h->d_counts.p, sizeof(uint32_t) * 2 * n_local, cudaMemcpyDeviceToDevice, h->stream));
+    LFX_SHARD_NCCL(s, nc->AllGather(s->d_send, s->d_recv + (size_t)(s->epoch & 1u) * s->slot_words, (size_t)s->width * 2, ncclUint32, s->comm, h->stream));
+  }
+  return LFX_OK;
+}
+
+int lfx_shard_finish(lfx_shard * s, lfx_shard_result * out)
+{
+  if (!s || !out) { return LFX_E_BAD_PARAM; }
+  if (s->epoch == 0) { return shard_fail(s, LFX_E_STATE, "no exchange has been started"); }
+  LFX_SHARD_CUDA(s, cudaSetDevice(s->h->device));
+  if (s->finished != s->epoch) { const int rc = shard_enqueue_scan(s); if (rc != LFX_OK) { return rc; } }
+  out->n_frames = s->n_frames;
+  out->first_frame = s->first;
+  out->last_frame = s->last;
+  out->d_counts_all = s->d_counts_all;
+  out->d_offsets_all = reinterpret_cast<const uint64_t *>(s->d_offsets_all);
+  return LFX_OK;
+}
+
+int lfx_shard_fetch(lfx_shard * s, uint32_t * counts_all, uint64_t * offsets_all)
+{
+  if (!s) { return LFX_E_BAD_PARAM; }
+  lfx_shard_result r;
+  const int rc = lfx_shard_finish(s, &r);
+  if (rc != LFX_OK) { return rc; }
+  lfx_handle * h = s->h;
+  uint32_t status = 0;
+  if (counts_all && s->n_frames) { LFX_SHARD_CUDA(s, cudaMemcpyAsync(counts_all, s->d_counts_all, sizeof(uint32_t) * 2 * s->n_frames, cudaMemcpyDeviceToHost, h->stream)); }
+  if (offsets_all) { LFX_SHARD_CUDA(s, cudaMemcpyAsync(offsets_all, s->d_offsets_all, sizeof(uint64_t) * 2 * (s->n_frames + 1), cudaMemcpyDeviceToHost, h->stream)); }
+  LFX_SHARD_CUDA(s, cudaMemcpyAsync(&status, s->d_status, sizeof(status), cudaMemcpyDeviceToHost, h->stream));
+  LFX_SHARD_CUDA(s, cudaStreamSynchronize(h->stream));
+  if (status != 0) { return shard_fail(s, LFX_E_STATE, "a peer rank did not publish its counts within 10 s"); }
+  return LFX_OK;
+}
+
+int lfx_shard_info(const lfx_shard * s, int * uses_peer_stores, int * nccl_ranks)
+{
+  if (!s) { return LFX_E_BAD_PARAM; }
+  if (uses_peer_stores) { *uses_peer_stores = s->p2p ? 1 : 0; }
+  if (nccl_ranks) { *nccl_ranks = s->nranks; }
+  return LFX_OK;
+}
+
+const char * lfx_shard_last_error(const lfx_shard * s) { return s ? s->err.c_str() : ""; }
+
+void lfx_shard_destroy(lfx_shard * s)
+{
+  if (!s) { return; }
+  if (s->h) { cudaSetDevice(s->h->device); if (s->h->stream) { cudaStreamSynchronize(s->h->stream); } }
+  for (int p = 0; p < s->world && p < lfxk::SHARD_MAX_WORLD; p++) { if (s->peer_opened[p]) { cudaIpcCloseMemHandle(s->peer_recv[p]); } }
+  cudaFree(s->d_recv); cudaFree(s->d_send); cudaFree(s->d_counts_all); cudaFree(s->d_offsets_all); cudaFree(s->d_status);
+  if (s->comm && nccl_api()->CommDestroy) { nccl_api()->CommDestroy(s->comm); }
+  delete s;
 }
 
 }  // extern "C"

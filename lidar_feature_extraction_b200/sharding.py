@@ -179,3 +179,132 @@ class ShardedExtraction:
         self.join()
         self.fe.synchronize()      # the counts (and the gather, enqueued on the same stream) are complete
         return global_offsets(self.counts_all.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same driver over the C ABI (include/lfx.h: lfx_shard_*). The exchange is the library's own: a one-CTA kernel that
+# stores the counts into every peer's receive buffer through peer-mapped memory (NVLink) and raises a flag; NCCL only
+# sets the group up. torch.distributed is not needed at all (the unique id can travel by any means); when a process
+# group exists it is used to hand the id around.
+
+class ShardError(RuntimeError):
+    pass
+
+
+class AbiShard:
+    """One rank of the sharded driver through lfx_shard_create / lfx_shard_exchange / lfx_shard_fetch.
+    ``unique_id``: the LFX_SHARD_ID_BYTES bytes rank 0 got from ``AbiShard.unique_id()`` (None: world == 1, or taken
+    from rank 0 through torch.distributed's default group when one is initialised)."""
+
+    def __init__(self, fe, n_frames: int, rank: int = 0, world: int = 1, unique_id: bytes | None = None):
+        import ctypes as C
+
+        from . import _native as N
+
+        self._lib = N.lib()
+        self.fe, self.n_frames, self.rank, self.world = fe, int(n_frames), int(rank), int(world)
+        self.lo, self.hi = shard_range(n_frames, rank, world)
+        if world > 1 and unique_id is None:
+            import torch.distributed as dist
+
+            if not dist.is_initialized():
+                raise ShardError("a unique id is needed (AbiShard.unique_id() on rank 0, handed to every rank)")
+            box = [self.unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            unique_id = box[0]
+        self._s = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), N.SHARD_ID_BYTES) if unique_id is not None else None
+        rc = self._lib.lfx_shard_create(fe.handle, buf, rank, world, self.n_frames, C.byref(self._s))
+        if rc != N.LFX_OK:
+            raise ShardError(f"lfx_shard_create: {N.STATUS_NAMES[rc]}: {self._lib.lfx_last_error(fe.handle).decode()}")
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+
+        from . import _native as N
+
+        buf = C.create_string_buffer(N.SHARD_ID_BYTES)
+        rc = N.lib().lfx_shard_unique_id(buf)
+        if rc != N.LFX_OK:
+            raise ShardError(f"lfx_shard_unique_id: {N.STATUS_NAMES[rc]}: {N.lib().lfx_last_error(None).decode()}")
+        return buf.raw
+
+    def _check(self, rc: int, what: str):
+        from . import _native as N
+
+        if rc != N.LFX_OK:
+            raise ShardError(f"{what}: {N.STATUS_NAMES[rc]}: {self._lib.lfx_shard_last_error(self._s).decode()}")
+
+    def step(self, views, keep=None):
+        """Extraction of this rank's shard + publication of its counts, both enqueued on the handle's stream."""
+        res = self.fe.extract_views(views, keep=keep)
+        self._check(self._lib.lfx_shard_exchange(self._s), "lfx_shard_exchange")
+        return res
+
+    def exchange(self):
+        self._check(self._lib.lfx_shard_exchange(self._s), "lfx_shard_exchange")
+
+    def finish(self):
+        """Enqueue the consumer side of the last exchange; returns the device-side tables (lfx_shard_result)."""
+        import ctypes as C
+
+        from . import _native as N
+
+        r = N.ShardResult()
+        self._check(self._lib.lfx_shard_finish(self._s, C.byref(r)), "lfx_shard_finish")
+        return r
+
+    def join(self):
+        self.finish()
+
+    def fetch(self):
+        """(counts [n_frames, 2] uint32, offsets [n_frames + 1, 2] uint64) of the last exchange, frame order; synchronises."""
+        counts = np.zeros((self.n_frames, 2), np.uint32)
+        offsets = np.zeros((self.n_frames + 1, 2), np.uint64)
+        self._check(self._lib.lfx_shard_fetch(self._s, counts.ctypes.data, offsets.ctypes.data), "lfx_shard_fetch")
+        return counts, offsets
+
+    def offsets(self) -> np.ndarray:
+        return self.fetch()[1].astype(np.int64)
+
+    def info(self) -> dict:
+        import ctypes as C
+
+        p2p, n = C.c_int(0), C.c_int(0)
+        self._check(self._lib.lfx_shard_info(self._s, C.byref(p2p), C.byref(n)), "lfx_shard_info")
+        return {"exchange": "peer stores over NVLink" if p2p.value else "ncclAllGather", "nccl_ranks": int(n.value)}
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._lib.lfx_shard_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def local_group(extractions, n_frames: int) -> list:
+    """All ranks in this process (lfx_shard_create_local): one AbiShard per FeatureExtraction, rank = position."""
+    import ctypes as C
+
+    from . import _native as N
+
+    lib = N.lib()
+    world = len(extractions)
+    hs = (C.c_void_p * world)(*[fe.handle for fe in extractions])
+    out = (C.c_void_p * world)()
+    rc = lib.lfx_shard_create_local(hs, world, int(n_frames), out)
+    if rc != N.LFX_OK:
+        raise ShardError(f"lfx_shard_create_local: {N.STATUS_NAMES[rc]}: {lib.lfx_last_error(extractions[0].handle).decode()}")
+    shards = []
+    for g, fe in enumerate(extractions):
+        s = AbiShard.__new__(AbiShard)
+        s._lib, s.fe, s.n_frames, s.rank, s.world = lib, fe, int(n_frames), g, world
+        s.lo, s.hi = shard_range(n_frames, g, world)
+        s._s = C.c_void_p(out[g])
+        shards.append(s)
+    return shards

@@ -120,3 +120,124 @@ def test_sharded_extraction_two_gpus_nccl(tmp_path, oracle, overlap):
         want.append([len(r.edge_idx), len(r.surface_idx)])
     for r in range(2):
         assert np.load(tmp_path / f"gpu_counts_{r}.npy").tolist() == want
+
+
+# ---- the C-ABI driver (lfx_shard_*): NCCL set-up, counts pushed through peer-mapped memory --------------------------
+
+def _oracle_counts(n_frames, oracle):
+    from lidar_feature_extraction_b200 import synth
+    from oracle import binding as ob
+
+    sp = synth.spec("vlp16")
+    want = []
+    for f in range(n_frames):
+        r = oracle.extract_scan(synth.scan_host(sp, f), ob.default_params())
+        want.append([len(r.edge_idx), len(r.surface_idx)])
+    return np.array(want, np.uint32)
+
+
+@pytest.mark.gpu
+def test_abi_shard_single_rank(oracle):
+    """world == 1 goes through the same kernels (a group of one)."""
+    import torch
+
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, synth
+
+    sp = synth.spec("vlp16")
+    n_frames = 3
+    with FeatureExtraction(HyperParameters(), device=0) as fe:
+        drv = sharding.AbiShard(fe, n_frames)
+        clouds = [torch.from_numpy(synth.scan_host(sp, f)).cuda() for f in range(n_frames)]
+        for _ in range(3):
+            drv.step([fe.wire_view(c) for c in clouds], keep=clouds)
+        counts, offsets = drv.fetch()
+        want = _oracle_counts(n_frames, oracle)
+        assert np.array_equal(counts, want)
+        assert np.array_equal(offsets, sharding.global_offsets(want).astype(np.uint64))
+        drv.close()
+
+
+@pytest.mark.gpu
+def test_abi_shard_local_group_two_gpus(oracle):
+    """Both ranks in this process (lfx_shard_create_local): 5 frames over 2 GPUs, several batches back to back."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, synth
+
+    sp = synth.spec("vlp16")
+    n_frames = 5
+    fes = [FeatureExtraction(HyperParameters(), device=g) for g in range(2)]
+    shards = sharding.local_group(fes, n_frames)
+    assert shards[0].info()["nccl_ranks"] == 2
+    assert shards[0].info()["exchange"].startswith("peer stores")
+    clouds = [[torch.from_numpy(synth.scan_host(sp, f)).to(f"cuda:{g}") for f in range(s.lo, s.hi)] for g, s in enumerate(shards)]
+    for _ in range(4):
+        for g, s in enumerate(shards):
+            s.step([fes[g].wire_view(c) for c in clouds[g]], keep=clouds[g])
+    want = _oracle_counts(n_frames, oracle)
+    for s in shards:
+        s.finish()
+    for s in shards:
+        counts, offsets = s.fetch()
+        assert np.array_equal(counts, want), s.rank
+        assert np.array_equal(offsets, sharding.global_offsets(want).astype(np.uint64))
+    for s in shards:
+        s.close()
+    for fe in fes:
+        fe.close()
+
+
+def _abi_worker(rank, world, out_dir, id_path, exchange):
+    import time
+
+    if exchange == "nccl":
+        os.environ["LFX_SHARD_EXCHANGE"] = "nccl"
+    import torch
+
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, synth
+
+    torch.cuda.set_device(rank)
+    # the unique id travels through a file: the C-ABI driver needs no torch.distributed
+    if rank == 0:
+        uid = sharding.AbiShard.unique_id()
+        with open(id_path + ".tmp", "wb") as f:
+            f.write(uid)
+        os.replace(id_path + ".tmp", id_path)
+    else:
+        for _ in range(600):
+            if os.path.exists(id_path):
+                break
+            time.sleep(0.05)
+        uid = open(id_path, "rb").read()
+    n_frames = 5
+    sp = synth.spec("vlp16")
+    fe = FeatureExtraction(HyperParameters(), device=rank)
+    drv = sharding.AbiShard(fe, n_frames, rank, world, unique_id=uid)
+    clouds = [torch.from_numpy(synth.scan_host(sp, f)).to(f"cuda:{rank}") for f in range(drv.lo, drv.hi)]
+    for _ in range(4):
+        drv.step([fe.wire_view(c) for c in clouds], keep=clouds)
+    counts, offsets = drv.fetch()
+    np.save(os.path.join(out_dir, f"abi_counts_{rank}.npy"), counts)
+    np.save(os.path.join(out_dir, f"abi_info_{rank}.npy"), np.array([drv.info()["nccl_ranks"], int(drv.info()["exchange"].startswith("peer"))]))
+    drv.close()
+    fe.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_abi_shard_one_process_per_gpu(tmp_path, oracle, exchange):
+    """One process per GPU (lfx_shard_create with a unique id): counts pushed into buffers mapped through CUDA IPC, or
+    (LFX_SHARD_EXCHANGE=nccl) gathered by ncclAllGather."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    mp.spawn(_abi_worker, args=(2, str(tmp_path), str(tmp_path / "nccl_id.bin"), exchange), nprocs=2, join=True)
+    want = _oracle_counts(5, oracle)
+    for r in range(2):
+        assert np.array_equal(np.load(tmp_path / f"abi_counts_{r}.npy"), want)
+        info = np.load(tmp_path / f"abi_info_{r}.npy")
+        assert info[0] == 2 and info[1] == (1 if exchange == "p2p" else 0)
