@@ -661,7 +661,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         nbytes = n_points * 32
-        hptr = lib.lfx_host_alloc(nbytes)
+        numa = C.c_int(-1)
+        hptr = lib.lfx_host_alloc_on(fe.handle, nbytes, C.byref(numa))   # pinned, on the NUMA node of this rank's GPU
         assert hptr, "pinned allocation failed"
         lib.lfx_memcpy_d2h(fe.handle, hptr, d_in.data_ptr(), nbytes)
         host_views = [FeatureExtraction.wire_view((hptr + int(offs[s]) * 32, sizes[s])) for s in range(scans_per_gpu)]
@@ -669,8 +670,8 @@ def main():
             v.memory = N.LFX_MEM_HOST
         host_views = FeatureExtraction.view_array(host_views)
         cap = n_points
-        h_edge = lib.lfx_host_alloc(16 * max(n_feat, 1) * 2)
-        h_surf = lib.lfx_host_alloc(16 * max(n_feat, 1) * 2)
+        h_edge = lib.lfx_host_alloc_on(fe.handle, 16 * max(n_feat, 1) * 2, None)
+        h_surf = lib.lfx_host_alloc_on(fe.handle, 16 * max(n_feat, 1) * 2, None)
         h_counts = np.zeros((scans_per_gpu, 2), np.uint32)
         h_offsets = np.zeros((scans_per_gpu + 1, 2), np.uint32)
 
@@ -705,7 +706,8 @@ def main():
             ms_e2e = float(t.item())
         d2h = int(h_counts.nbytes + h_offsets.nbytes + 16 * (int(h_offsets[-1, 0]) + int(h_offsets[-1, 1])))
         e2e = {"value": n_points * world / (ms_e2e / k_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": d2h, "steps": k_e2e, "ms_per_step": ms_e2e / k_e2e}
+               "d2h_bytes_per_step": d2h, "steps": k_e2e, "ms_per_step": ms_e2e / k_e2e,
+               "host_buffers": f"pinned, NUMA node {numa.value} (node of the rank's GPU)" if numa.value >= 0 else "pinned (no NUMA node reported)"}
         lib.lfx_host_free(hptr)
         lib.lfx_host_free(h_edge)
         lib.lfx_host_free(h_surf)

@@ -340,6 +340,10 @@ int lfx_pose_diff_is_small(const lfx_pose *pose0, const lfx_pose *pose1, double 
 /* Pinned host memory so that H2D/D2H run at full PCIe speed. */
 void *lfx_host_alloc(size_t bytes);
 void lfx_host_free(void *p);
+/* Pinned host memory on the NUMA node of the handle's GPU (sysfs numa_node of its PCI device; set_mempolicy around the
+ * allocation). *numa_node_out (may be NULL): the node the pages were bound to, -1 if the platform gave none. Use it
+ * for the scan buffers of a rank that feeds its GPU from host memory; free with lfx_host_free. */
+void *lfx_host_alloc_on(lfx_handle *h, size_t bytes, int *numa_node_out);
 int lfx_device_alloc(lfx_handle *h, size_t bytes, void **out);
 int lfx_device_free(lfx_handle *h, void *p);
 int lfx_memcpy_h2d(lfx_handle *h, void *dst_device, const void *src_host, size_t bytes);
@@ -399,6 +403,28 @@ int lfx_synth_scan_host(const lfx_synth_spec *spec, uint64_t frame, void *out, u
 /* device generator (no drop-outs): n_scans consecutive frames, each n_rings*n_cols*32 bytes, contiguous */
 int lfx_synth_batch_device(lfx_handle *h, const lfx_synth_spec *spec, uint64_t first_frame, int n_scans,
                            void *d_out);
+
+/* ------------------------------------------------------------------ localization residual build
+ * First slice of the consumer's hot loop: what Edge<..>::Make (localization/include/lidar_feature_localization/
+ * edge.hpp:88-124) and Surface<..>::MakeFromDownsampled (surface.hpp:116-139) compute for every feature of a scan in
+ * every iteration of the optimiser: the n_neighbors nearest points of the edge / surface map (kdtree.cpp:42-55), the
+ * line (mean + principal axis of the neighbours) or plane (least squares X w = -1) through them, and the feature's
+ * Jacobian block and residual. The neighbour search is exact and returns the same index lists as the reference's
+ * kd-tree (ascending distance; nanoflann's L2 over doubles). The voxel down-sampling of the surface scan
+ * (surface.hpp:106-112) is PCL's and stays with the caller: pass the down-sampled scan.
+ * Layouts: map and scan points are 16-byte x,y,z,1.0f (pcl::PointXYZ, what lfx_extract_* emit and lfx_map_* hold);
+ * point_to_map: rotation as quaternion (x,y,z,w) + translation; edge Jacobians [n][3][7] row major with columns
+ * (q_w, q_x, q_y, q_z, t_x, t_y, t_z) as MakeEdgeJacobianRow (edge.cpp:64-73), residuals [n][3]; surface Jacobians
+ * [n][7] (MakeJacobianRow, surface.hpp:84-92), residuals [n]; neighbors (optional) [n][n_neighbors] map indices.
+ * Synchronous; outputs are host arrays. */
+#define LFX_LOC_EDGE 0
+#define LFX_LOC_SURFACE 1
+int lfx_loc_set_map(lfx_handle *h, int kind, const float *xyz4, uint64_t n_points, int memory /* LFX_MEM_* */);
+int lfx_loc_edge(lfx_handle *h, const float *scan_xyz4, uint32_t n, int memory, const lfx_pose *point_to_map, int n_neighbors,
+                 double *jacobians, double *residuals, uint32_t *neighbors);
+int lfx_loc_surface(lfx_handle *h, const float *scan_xyz4, uint32_t n, int memory, const lfx_pose *point_to_map, int n_neighbors,
+                    double *jacobians, double *residuals, uint32_t *neighbors);
+int lfx_loc_release(lfx_handle *h);   /* frees the maps and work buffers (also done by lfx_destroy) */
 
 /* ------------------------------------------------------------------ multi-GPU driver (SURVEY.md 8(b) "Threading", 8(e))
  * Scans are independent (the reference's callback is const and stateless, feature_extraction.cpp:92,173-175): a

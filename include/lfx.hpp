@@ -222,6 +222,43 @@ private:
   lfx_handle * h_;
 };
 
+// The localization consumer's residual build (LOAMOptimizationProblem::Make, loam_optimization_problem.hpp:62-84, for
+// maps held on the device): Edge / Surface return the Jacobian blocks and residuals of all features of a scan at once.
+class LoamProblem
+{
+public:
+  // maps: 16-byte x,y,z,1 points (pcl::PointXYZ), host or device memory
+  LoamProblem(FeatureExtraction & fe, const float * edge_map, uint64_t n_edge, const float * surface_map, uint64_t n_surface,
+              int n_neighbors = 15, bool device_memory = false)
+  : h_(fe.handle()), k_(n_neighbors)
+  {
+    const int mem = device_memory ? LFX_MEM_DEVICE : LFX_MEM_HOST;
+    Check(lfx_loc_set_map(h_, LFX_LOC_EDGE, edge_map, n_edge, mem));
+    Check(lfx_loc_set_map(h_, LFX_LOC_SURFACE, surface_map, n_surface, mem));
+  }
+  // jacobians [n][3][7] (columns q_w,q_x,q_y,q_z,t_x,t_y,t_z), residuals [n][3]
+  void Edge(const float * scan, uint32_t n, const lfx_pose & point_to_map, std::vector<double> & jacobians, std::vector<double> & residuals,
+            bool device_memory = false)
+  {
+    jacobians.resize(static_cast<size_t>(n) * 21);
+    residuals.resize(static_cast<size_t>(n) * 3);
+    Check(lfx_loc_edge(h_, scan, n, device_memory ? LFX_MEM_DEVICE : LFX_MEM_HOST, &point_to_map, k_, jacobians.data(), residuals.data(), nullptr));
+  }
+  // jacobians [n][7], residuals [n]; `scan` is the surface scan AFTER its voxel down-sampling (surface.hpp:106-112)
+  void Surface(const float * scan, uint32_t n, const lfx_pose & point_to_map, std::vector<double> & jacobians, std::vector<double> & residuals,
+               bool device_memory = false)
+  {
+    jacobians.resize(static_cast<size_t>(n) * 7);
+    residuals.resize(n);
+    Check(lfx_loc_surface(h_, scan, n, device_memory ? LFX_MEM_DEVICE : LFX_MEM_HOST, &point_to_map, k_, jacobians.data(), residuals.data(), nullptr));
+  }
+
+private:
+  void Check(int rc) { if (rc != LFX_OK) { throw Error(rc, lfx_last_error(h_)); } }
+  lfx_handle * h_;
+  int k_;
+};
+
 // One rank of the multi-GPU driver ("multi-GPU driver owns 8 handles + NCCL comm"; 8(e)): frames are
 // sharded by index, rank g of G owning [g F / G, (g + 1) F / G). Per batch: fe.ExtractBatch(this rank's scans), then
 // Exchange(); Fetch() (or Finish() for the device-side tables) whenever the frame-ordered global tables are needed.

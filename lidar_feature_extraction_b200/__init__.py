@@ -18,10 +18,11 @@ from .extraction import (  # noqa: F401
 )
 from .converter import ConvertError, PointTypeConverter  # noqa: F401
 from .mapping import MapBuilder, make_pose, pose_diff_is_sufficiently_small  # noqa: F401
+from .localization import LoamProblem  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = [
     "FeatureExtraction", "HyperParameters", "PointCloud2", "PointField", "ExtractionError", "default_params",
     "launch_yaml_params", "label_to_color", "synth", "POINT_STEP", "PointTypeConverter", "ConvertError", "MapBuilder", "make_pose",
-    "pose_diff_is_sufficiently_small",
+    "pose_diff_is_sufficiently_small", "LoamProblem",
 ]

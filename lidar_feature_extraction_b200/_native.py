@@ -27,6 +27,7 @@ LFX_RING_U8, LFX_RING_U16, LFX_RING_U32 = 2, 4, 6
 LFX_RING_OK, LFX_RING_SPARSE, LFX_RING_SKIPPED, LFX_RING_TOO_LONG = range(4)
 LFX_WORLD_ROOM, LFX_WORLD_TUNNEL = 0, 1
 LFX_TOPIC_SCAN_EDGE, LFX_TOPIC_SCAN_SURFACE, LFX_TOPIC_COLORED_SCAN = 0, 1, 2
+LFX_LOC_EDGE, LFX_LOC_SURFACE = 0, 1
 
 
 class Params(C.Structure):
@@ -225,6 +226,8 @@ def lib() -> C.CDLL:
     L.lfx_label_to_color.argtypes = [C.c_uint8, C.c_void_p]
     L.lfx_host_alloc.argtypes = [C.c_size_t]
     L.lfx_host_alloc.restype = C.c_void_p
+    L.lfx_host_alloc_on.argtypes = [H, C.c_size_t, C.POINTER(C.c_int)]
+    L.lfx_host_alloc_on.restype = C.c_void_p
     L.lfx_host_free.argtypes = [C.c_void_p]
     L.lfx_host_free.restype = None
     L.lfx_device_alloc.argtypes = [H, C.c_size_t, C.POINTER(C.c_void_p)]
@@ -254,6 +257,10 @@ def lib() -> C.CDLL:
     L.lfx_synth_named.argtypes = [C.c_char_p, C.POINTER(SynthSpec)]
     L.lfx_synth_scan_host.argtypes = [C.POINTER(SynthSpec), C.c_uint64, C.c_void_p, C.POINTER(C.c_uint32)]
     L.lfx_synth_batch_device.argtypes = [H, C.POINTER(SynthSpec), C.c_uint64, C.c_int, C.c_void_p]
+    L.lfx_loc_set_map.argtypes = [H, C.c_int, C.c_void_p, C.c_uint64, C.c_int]
+    for fn in (L.lfx_loc_edge, L.lfx_loc_surface):
+        fn.argtypes = [H, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(Pose), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lfx_loc_release.argtypes = [H]
     S = C.c_void_p
     L.lfx_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.lfx_shard_unique_id.argtypes = [C.c_void_p]

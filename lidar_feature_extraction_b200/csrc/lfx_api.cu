@@ -26,9 +26,11 @@
 #include "lfx_color.cuh"
 #include "lfx_map.cuh"
 #include "lfx_shard.cuh"
+#include "lfx_loc.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is loaded at run time (lfx_shard_*), single-GPU users do not need it
+#include <sys/syscall.h>
 #include <unistd.h>
 
 using namespace lfxk;
@@ -154,6 +156,8 @@ struct lfx_handle
   uint64_t total_points = 0;
   uint32_t total_tiles = 0;
   bool have_batch = false;
+
+  struct LocState * loc = nullptr;   // localization residual build (lfx_loc_*), created on first use
 
   bool timing = false;
   bool timing_in_graph = false;   // stage events as external event-record nodes of the captured graph
@@ -574,9 +578,12 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   return LFX_OK;
 }
 
+extern "C" int lfx_loc_release(lfx_handle * h);
+
 void lfx_destroy(lfx_handle * h)
 {
   if (!h) { return; }
+  lfx_loc_release(h);
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); }
   drop_graphs(h);
@@ -956,6 +963,44 @@ void * lfx_host_alloc(size_t bytes)
 }
 
 void lfx_host_free(void * p) { if (p) { cudaFreeHost(p); } }
+
+// NUMA node the handle's GPU hangs off (sysfs), or -1
+static int gpu_numa_node(int device)
+{
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char * c = bus; *c; c++) { if (*c >= 'A' && *c <= 'F') { *c = (char)(*c - 'A' + 'a'); } }   // sysfs spells it in lower case
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE * f = fopen(path.c_str(), "r");
+  if (!f) { return -1; }
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) { node = -1; }
+  fclose(f);
+  return node;
+}
+
+void * lfx_host_alloc_on(lfx_handle * h, size_t bytes, int * numa_node_out)
+{
+  // Pinned memory whose pages sit on the NUMA node of the handle's GPU: with one process per GPU on a two-socket host,
+  // buffers that all end up on the node the processes happened to start on make every other GPU's DMA cross the
+  // socket interconnect (r01s: 8 ranks reached 160 GB/s of host-to-device copies together, 51 GB/s alone).
+  // set_mempolicy(MPOL_PREFERRED) around the allocation; the raw system call, so that libnuma is not a dependency.
+  const int node = h ? gpu_numa_node(h->device) : -1;
+  if (numa_node_out) { *numa_node_out = node; }
+  bool bound = false;
+  if (node >= 0 && node < 1024) {
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1024ul + 1) == 0;
+  }
+  void * p = nullptr;
+  if (h) { cudaSetDevice(h->device); }
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { p = nullptr; cudaGetLastError(); }
+  if (p) { memset(p, 0, bytes ? bytes : 1); }   // (pinning allocates the pages; this only makes sure of it while the policy holds)
+  if (bound) { syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul); }
+  if (numa_node_out && !bound) { *numa_node_out = -1; }
+  return p;
+}
 
 int lfx_device_alloc(lfx_handle * h, size_t bytes, void ** out)
 {
@@ -1984,6 +2029,156 @@ void lfx_shard_destroy(lfx_shard * s)
   cudaFree(s->d_recv); cudaFree(s->d_send); cudaFree(s->d_counts_all); cudaFree(s->d_offsets_all); cudaFree(s->d_status);
   if (s->comm && nccl_api()->CommDestroy) { nccl_api()->CommDestroy(s->comm); }
   delete s;
+}
+
+}  // extern "C"
+
+// ====================================================================== localization residual build
+
+struct LocMap { double * x = nullptr, * y = nullptr, * z = nullptr; uint64_t n = 0, cap = 0; };
+
+struct LocState
+{
+  LocMap map[2];
+  DevBuf<float4> d_scan;
+  DevBuf<uint32_t> d_nbr;
+  DevBuf<double> d_d2, d_J, d_r;
+};
+
+namespace
+{
+
+LocState & loc_state(lfx_handle * h)
+{
+  if (!h->loc) { h->loc = new LocState(); }
+  return *h->loc;
+}
+
+lfxk::LocPose loc_pose(const lfx_pose & p)
+{
+  lfxk::LocPose T;
+  // Eigen::Quaterniond(w, x, y, z).toRotationMatrix()
+  const double x = p.orientation[0], y = p.orientation[1], z = p.orientation[2], w = p.orientation[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  T.r[0] = 1.0 - (tyy + tzz); T.r[1] = txy - twz; T.r[2] = txz + twy;
+  T.r[3] = txy + twz; T.r[4] = 1.0 - (txx + tzz); T.r[5] = tyz - twx;
+  T.r[6] = txz - twy; T.r[7] = tyz + twx; T.r[8] = 1.0 - (txx + tyy);
+  T.t[0] = p.position[0]; T.t[1] = p.position[1]; T.t[2] = p.position[2];
+  T.q[0] = x; T.q[1] = y; T.q[2] = z; T.q[3] = w;
+  return T;
+}
+
+template<int K>
+void launch_knn(lfx_handle * h, const LocMap & m, const float4 * scan, uint32_t n, const lfxk::LocPose & T, uint32_t * nbr, double * d2)
+{
+  const unsigned grid = (n + lfxk::LOC_KNN_WARPS - 1) / lfxk::LOC_KNN_WARPS;
+  lfxk::k_loc_knn<K><<<grid, lfxk::LOC_KNN_WARPS * 32, 0, h->stream>>>(m.x, m.y, m.z, (uint32_t)m.n, scan, n, T, nbr, d2);
+}
+
+int loc_run(lfx_handle * h, int kind, const float * scan_xyz4, uint32_t n, int memory, const lfx_pose * pose, int k, double * J_out,
+            double * r_out, uint32_t * nbr_out)
+{
+  if (!h || !pose || (n > 0 && !scan_xyz4) || (kind != LFX_LOC_EDGE && kind != LFX_LOC_SURFACE)) { return LFX_E_BAD_PARAM; }
+  if (k < 1 || k > lfxk::LOC_MAX_K) { return fail(h, LFX_E_BAD_PARAM, "n_neighbors must be in 1..16"); }
+  if (kind == LFX_LOC_SURFACE && k < 3) { return fail(h, LFX_E_BAD_PARAM, "a plane needs at least three neighbours"); }
+  LocState & st = loc_state(h);
+  const LocMap & m = st.map[kind];
+  if (m.n < (uint64_t)k) { return fail(h, LFX_E_STATE, "the map holds fewer points than n_neighbors (lfx_loc_set_map)"); }
+  if (m.n > 0xFFFFFFF0ull) { return fail(h, LFX_E_CAPACITY, "map too large for 32-bit neighbour indices"); }
+  if (n == 0) { return LFX_OK; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  int rc;
+  const float4 * d_scan = reinterpret_cast<const float4 *>(scan_xyz4);
+  if (memory == LFX_MEM_HOST) {
+    if ((rc = ensure(h, st.d_scan, n, nullptr))) { return rc; }
+    LFX_CUDA(h, cudaMemcpyAsync(st.d_scan.p, scan_xyz4, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    d_scan = st.d_scan.p;
+  }
+  const int jw = kind == LFX_LOC_EDGE ? 21 : 7, rw = kind == LFX_LOC_EDGE ? 3 : 1;
+  if ((rc = ensure(h, st.d_nbr, (size_t)n * k, nullptr)) || (rc = ensure(h, st.d_d2, (size_t)n * k, nullptr)) ||
+      (rc = ensure(h, st.d_J, (size_t)n * jw, nullptr)) || (rc = ensure(h, st.d_r, (size_t)n * rw, nullptr))) { return rc; }
+  const lfxk::LocPose T = loc_pose(*pose);
+  switch (k) {   // the per-lane candidate lists live in registers: k is a template parameter
+#define LFX_KNN_CASE(KK) case KK: launch_knn<KK>(h, m, d_scan, n, T, st.d_nbr.p, st.d_d2.p); break;
+    LFX_KNN_CASE(1) LFX_KNN_CASE(2) LFX_KNN_CASE(3) LFX_KNN_CASE(4) LFX_KNN_CASE(5) LFX_KNN_CASE(6) LFX_KNN_CASE(7) LFX_KNN_CASE(8)
+    LFX_KNN_CASE(9) LFX_KNN_CASE(10) LFX_KNN_CASE(11) LFX_KNN_CASE(12) LFX_KNN_CASE(13) LFX_KNN_CASE(14) LFX_KNN_CASE(15) LFX_KNN_CASE(16)
+#undef LFX_KNN_CASE
+  }
+  LFX_CUDA(h, cudaGetLastError());
+  lfxk::LocArgs a;
+  a.mx = m.x; a.my = m.y; a.mz = m.z; a.scan = d_scan; a.nbr = st.d_nbr.p; a.n = n; a.k = k; a.T = T; a.J = st.d_J.p; a.r = st.d_r.p;
+  if (kind == LFX_LOC_EDGE) { lfxk::k_loc_edge<<<(n + 127) / 128, 128, 0, h->stream>>>(a); }
+  else { lfxk::k_loc_surface<<<(n + 127) / 128, 128, 0, h->stream>>>(a); }
+  LFX_CUDA(h, cudaGetLastError());
+  h->launches += 2;
+  if (J_out) { LFX_CUDA(h, cudaMemcpyAsync(J_out, st.d_J.p, sizeof(double) * (size_t)n * jw, cudaMemcpyDeviceToHost, h->stream)); }
+  if (r_out) { LFX_CUDA(h, cudaMemcpyAsync(r_out, st.d_r.p, sizeof(double) * (size_t)n * rw, cudaMemcpyDeviceToHost, h->stream)); }
+  if (nbr_out) { LFX_CUDA(h, cudaMemcpyAsync(nbr_out, st.d_nbr.p, sizeof(uint32_t) * (size_t)n * k, cudaMemcpyDeviceToHost, h->stream)); }
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return LFX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lfx_loc_set_map(lfx_handle * h, int kind, const float * xyz4, uint64_t n, int memory)
+{
+  if (!h || (n > 0 && !xyz4) || (kind != LFX_LOC_EDGE && kind != LFX_LOC_SURFACE)) { return LFX_E_BAD_PARAM; }
+  LFX_CUDA(h, cudaSetDevice(h->device));
+  LocState & st = loc_state(h);
+  LocMap & m = st.map[kind];
+  if (n > m.cap) {
+    LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(m.x); cudaFree(m.y); cudaFree(m.z);
+    m.x = m.y = m.z = nullptr; m.cap = 0;
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.x), sizeof(double) * n));
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.y), sizeof(double) * n));
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.z), sizeof(double) * n));
+    m.cap = n;
+  }
+  m.n = n;
+  if (n == 0) { return LFX_OK; }
+  const float4 * src = reinterpret_cast<const float4 *>(xyz4);
+  float4 * tmp = nullptr;
+  if (memory == LFX_MEM_HOST) {
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&tmp), sizeof(float4) * n));
+    LFX_CUDA(h, cudaMemcpyAsync(tmp, xyz4, sizeof(float4) * n, cudaMemcpyHostToDevice, h->stream));
+    src = tmp;
+  }
+  lfxk::k_loc_soa<<<h->num_sms * 4, 256, 0, h->stream>>>(src, n, m.x, m.y, m.z);
+  LFX_CUDA(h, cudaGetLastError());
+  h->launches += 1;
+  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (tmp) { cudaFree(tmp); }
+  return LFX_OK;
+}
+
+int lfx_loc_edge(lfx_handle * h, const float * scan_xyz4, uint32_t n, int memory, const lfx_pose * point_to_map, int n_neighbors,
+                 double * jacobians, double * residuals, uint32_t * neighbors)
+{
+  return loc_run(h, LFX_LOC_EDGE, scan_xyz4, n, memory, point_to_map, n_neighbors, jacobians, residuals, neighbors);
+}
+
+int lfx_loc_surface(lfx_handle * h, const float * scan_xyz4, uint32_t n, int memory, const lfx_pose * point_to_map, int n_neighbors,
+                    double * jacobians, double * residuals, uint32_t * neighbors)
+{
+  return loc_run(h, LFX_LOC_SURFACE, scan_xyz4, n, memory, point_to_map, n_neighbors, jacobians, residuals, neighbors);
+}
+
+int lfx_loc_release(lfx_handle * h)
+{
+  if (!h) { return LFX_E_BAD_PARAM; }
+  if (!h->loc) { return LFX_OK; }
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); }
+  LocState & st = *h->loc;
+  for (LocMap & m : st.map) { cudaFree(m.x); cudaFree(m.y); cudaFree(m.z); }
+  cudaFree(st.d_scan.p); cudaFree(st.d_nbr.p); cudaFree(st.d_d2.p); cudaFree(st.d_J.p); cudaFree(st.d_r.p);
+  delete h->loc;
+  h->loc = nullptr;
+  return LFX_OK;
 }
 
 }  // extern "C"
