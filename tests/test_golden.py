@@ -13,7 +13,7 @@ from helpers import compare_scan, oracle_params
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
-                  if not os.path.basename(p).startswith("convert_"))  # converter fixtures: test_convert_oracle.py
+                  if not os.path.basename(p).startswith(("convert_", "loc_")))  # converter / localization fixtures have their own tests
 PARAMSETS = {
     "default": dict(),
     "yaml": dict(padding=2, neighbor_degree_threshold=3.0, edge_threshold=50.0, max_range=1000.0),
