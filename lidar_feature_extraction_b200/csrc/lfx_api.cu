@@ -70,6 +70,7 @@ struct lfx_handle
   int device = 0;
   int num_sms = 0;
   int ring_grid = 0, pack_grid = 0;
+  int tile = TILE_SMALL;   // points per ingest tile (TILE_BIG when the scatter's shared memory fits)
   size_t ring_smem = 0;
   int cap = 0;
   int ring_threads = 0;
@@ -334,12 +335,22 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   k_general_list<<<1, 1024, 0, h->stream>>>(h->d_scans.p, n_scans, h->d_scan_flags.p, h->d_gen_scan.p, h->d_gen_tile_base.p,
                                             h->d_tile_owner.p, h->d_counters);
   const int ingest_grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_tiles, 1u), (uint32_t)h->ingest_grid);
-  k_ring_hist<<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
-    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
+  if (h->tile == TILE_BIG) {
+    k_ring_hist<TILE_BIG><<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
+      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
+  } else {
+    k_ring_hist<TILE_SMALL><<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
+      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
+  }
   k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
     h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, max_rings, h->params.padding, h->cap);
-  k_ring_scatter<<<ingest_grid, INGEST_THREADS, scatter_smem_bytes(max_rings), h->stream>>>(
-    h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
+  if (h->tile == TILE_BIG) {
+    k_ring_scatter<TILE_BIG><<<ingest_grid, INGEST_THREADS, scatter_smem_bytes(max_rings, TILE_BIG), h->stream>>>(
+      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
+  } else {
+    k_ring_scatter<TILE_SMALL><<<ingest_grid, INGEST_THREADS, scatter_smem_bytes(max_rings, TILE_SMALL), h->stream>>>(
+      h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
+  }
   // ---- bucketed rings that are rotated monotone sequences: sector kernel through the index list; the rest
   //      (and every ring whose hypothesis fails there) form the work list of the per-ring kernel
   RingProbeArgs rp;
@@ -532,12 +543,15 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   int tmax = 0;
   h->ring_kernel = pick_ring_kernel(params->padding, h->ring_threads, &tmax);
   if ((e = cudaFuncSetAttribute(h->ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ring_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(rings)"); }
-  const size_t scatter_smem = scatter_smem_bytes(h->opt.max_rings);
+  // ingest tile: the big one while three scatter CTAs still fit an SM
+  h->tile = scatter_smem_bytes(h->opt.max_rings, TILE_BIG) * 3 <= (size_t)prop.sharedMemPerMultiprocessor ? TILE_BIG : TILE_SMALL;
+  const size_t scatter_smem = scatter_smem_bytes(h->opt.max_rings, h->tile);
   if (scatter_smem > 48 * 1024) {
-    if ((e = cudaFuncSetAttribute(k_ring_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter)"); }
+    e = h->tile == TILE_BIG ? cudaFuncSetAttribute(k_ring_scatter<TILE_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem)
+                            : cudaFuncSetAttribute(k_ring_scatter<TILE_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
+    if (e != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter)"); }
   }
   int occ = 0;
-  // bitmap scatter: 390 B of shared memory per ring id; above ~500 ring ids the match-based scatter takes over
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->ring_kernel, h->ring_threads, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
   h->ring_grid = h->num_sms * std::max(occ, 1);
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_copy, 256, 0)) != cudaSuccess) { return bail(e, "occupancy(pack)"); }
@@ -649,7 +663,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
       return fail(h, LFX_E_BAD_LAYOUT, "x/y/z must be 4-byte aligned and ring naturally aligned");
     }
     total_points += v.n_points;
-    total_tiles += (v.n_points + TILE - 1) / TILE;
+    total_tiles += (v.n_points + h->tile - 1) / h->tile;
     if (v.memory == LFX_MEM_HOST) { input_bytes += ((size_t)v.n_points * v.point_step + 15) & ~(size_t)15; }
   }
   if (total_points >= 0xFFFF0000ull) { return fail(h, LFX_E_CAPACITY, "batch exceeds 2^32 points"); }
@@ -750,7 +764,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
     d.off_x = v.off_x; d.off_y = v.off_y; d.off_z = v.off_z; d.off_ring = v.off_ring;
     d.ring_dt = v.ring_datatype;
     d.tile_base = tb;
-    d.n_tiles = (v.n_points + TILE - 1) / TILE;
+    d.n_tiles = (v.n_points + h->tile - 1) / h->tile;
     d.ring16_lo = d.ring16_hi = 0;
     if (v.memory != LFX_MEM_HOST && h->have_conv && h->d_conv_out.p && v.point_step == 32 && v.off_ring == 20 && v.ring_datatype == LFX_RING_U16) {
       // a cloud the converter of this handle has just produced: its ring ids exist as a compact u16 array

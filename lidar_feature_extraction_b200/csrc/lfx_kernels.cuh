@@ -28,7 +28,9 @@
 namespace lfxk
 {
 
-constexpr int TILE = 2048;          // points per ingest tile
+// points per ingest tile: 8192 (fewer, better amortised tile iterations) when the scatter's shared memory allows it,
+// i.e. for max_rings <= 2048, else 2048; the kernels are templated on it, the host keeps the choice in the handle
+constexpr int TILE_BIG = 8192, TILE_SMALL = 2048;
 constexpr int INGEST_THREADS = 256; // 8 warps, 256 consecutive points each
 constexpr int MAX_PADDING = 15;     // selection windows live in 16-bit halves
 constexpr int MAX_BLOCKS = 64;
@@ -194,6 +196,7 @@ k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t 
 // kernels below so that the chain runs while the current tile is processed
 struct TileJob { uint32_t scan, tile, first, n_points; uint64_t point_base; const uint8_t * ring_ptr; uint32_t point_step, ring_dt; const uint16_t * src16; };
 
+template<int TILE>
 __device__ __forceinline__ TileJob load_tile_job(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
                                                  const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner, uint32_t t)
 {
@@ -213,6 +216,7 @@ __device__ __forceinline__ TileJob load_tile_job(const ScanDesc * __restrict__ s
   return j;
 }
 
+template<int TILE>
 __global__ void __launch_bounds__(INGEST_THREADS)
 k_ring_hist(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
             const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner, uint16_t * __restrict__ ring16,
@@ -224,10 +228,10 @@ k_ring_hist(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ g
   const uint32_t n_tiles = counters[C_GEN_TILES];
   uint32_t t = blockIdx.x;
   if (t >= n_tiles) { return; }
-  TileJob cur = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, t);
+  TileJob cur = load_tile_job<TILE>(scans, gen_scan, gen_tile_base, tile_owner, t);
   for (; t < n_tiles; t += gridDim.x) {
     const uint32_t tn = t + gridDim.x < n_tiles ? t + gridDim.x : t;
-    const TileJob nxt = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, tn);
+    const TileJob nxt = load_tile_job<TILE>(scans, gen_scan, gen_tile_base, tile_owner, tn);
     uint32_t rg[PER];
 #pragma unroll
     for (int c = 0; c < PER; c++) {
@@ -309,11 +313,12 @@ k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ s
 
 // shared memory: [8 warps][R] positions | [R] tile count | [R] tile offset | [R] bucket base | [TILE] sorted source
 // indices | [TILE] their rings (u16) | [8 warps][R] lane probes (bytes)
-__host__ __device__ inline size_t scatter_smem_bytes(int max_rings)
+__host__ __device__ inline size_t scatter_smem_bytes(int max_rings, int tile)
 {
-  return (size_t)(INGEST_THREADS / 32) * max_rings * 5 + (size_t)max_rings * 12 + (size_t)TILE * 6;
+  return (size_t)(INGEST_THREADS / 32) * max_rings * 5 + (size_t)max_rings * 12 + (size_t)tile * 6;
 }
 
+template<int TILE>
 __global__ void __launch_bounds__(INGEST_THREADS)
 k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ gen_scan,
                const uint32_t * __restrict__ gen_tile_base, const uint32_t * __restrict__ tile_owner,
@@ -354,13 +359,13 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
     return r < R ? rings[(size_t)j.scan * R + r].offset + tile_hist[(size_t)j.tile * R + r] : 0u;
   };
   auto clamp_t = [&](uint32_t u) { return u < n_tiles ? u : n_tiles - 1; };
-  TileJob cur = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, t);
-  TileJob nxt = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, clamp_t(t + gridDim.x));
+  TileJob cur = load_tile_job<TILE>(scans, gen_scan, gen_tile_base, tile_owner, t);
+  TileJob nxt = load_tile_job<TILE>(scans, gen_scan, gen_tile_base, tile_owner, clamp_t(t + gridDim.x));
   uint32_t ring[CHUNKS], ring_n[CHUNKS];
   load_ids(cur, ring);
   uint32_t base0 = load_base(cur);
   for (; t < n_tiles; t += gridDim.x) {
-    const TileJob nxt2 = load_tile_job(scans, gen_scan, gen_tile_base, tile_owner, clamp_t(t + 2 * gridDim.x));
+    const TileJob nxt2 = load_tile_job<TILE>(scans, gen_scan, gen_tile_base, tile_owner, clamp_t(t + 2 * gridDim.x));
     load_ids(nxt, ring_n);
     const uint32_t base0_n = load_base(nxt);
     const uint32_t first = cur.first + warp * PER_WARP;
