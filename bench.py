@@ -342,30 +342,49 @@ def stage_times(fe, views, keep, mode: int, sync: bool, iters: int):
     return np.array(rows[1:])
 
 
-def measure_workload(name: str, local_rank: int, dev, stream, steps: int, peak: float) -> dict:
-    """One of the other BASELINE.json configs, device-resident, single GPU: same timing rules as the headline (CUDA
-    events on the launching stream, >= 3 warm-up steps, inputs larger than L2), fewer extras."""
+def measure_workload(name: str, local_rank: int, dev, stream, steps: int, peak: float, rank: int = 0, world: int = 1) -> dict:
+    """One of the other BASELINE.json configs, device-resident: same timing rules as the headline (CUDA events on the
+    launching stream, >= 3 warm-up steps, inputs larger than L2), fewer extras. world > 1: every rank extracts its own
+    shard of world x scans frames and the per-scan counts are exchanged each step (lfx_shard_*); time = max over ranks,
+    value = all ranks' points / that time; the stage times and paths are rank 0's."""
     import torch
 
-    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, synth
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, sharding, synth
     from lidar_feature_extraction_b200 import _native as N
 
     sensor, scans = WORKLOADS[name]
     sp = synth.spec(sensor)
     lib = N.lib()
     fe = FeatureExtraction(HyperParameters(), device=local_rank, stream=stream.cuda_stream, max_rings=max(128, sp.n_rings))
-    d_in, sizes, _ = make_inputs(fe, lib, sp, 0, scans, dev)
+    d_in, sizes, _ = make_inputs(fe, lib, sp, rank * scans, scans, dev)
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n_points = int(offs[-1])
     views = FeatureExtraction.view_array(
         [FeatureExtraction.wire_view((d_in.data_ptr() + int(offs[s]) * 32, sizes[s])) for s in range(scans)])
+    shard = sharding.AbiShard(fe, world * scans, rank, world) if world > 1 else None
+
+    def step():
+        if shard is not None:
+            shard.step(views, keep=d_in)
+        else:
+            fe.extract_views(views, keep=d_in)
+
     for _ in range(3):
-        fe.extract_views(views, keep=d_in)
+        step()
+    if shard is not None:
+        shard.join()
     torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(steps):
-        fe.extract_views(views, keep=d_in)
+        step()
+    if shard is not None:
+        shard.join()
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
@@ -373,13 +392,26 @@ def measure_workload(name: str, local_rank: int, dev, stream, steps: int, peak: 
     lib.lfx_fetch_counts(fe.handle, counts.ctypes.data, offsets.ctypes.data)
     n_feat = int(offsets[-1, 0]) + int(offsets[-1, 1])
     alg = 32 * n_points + n_points + 16 * n_feat + 8 * scans
+    if world > 1:
+        t = torch.tensor([ms, float(n_points), float(alg)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0].item())
+        n_points_all, alg_all = int(t[1].item()), int(t[2].item())
+    else:
+        n_points_all, alg_all = n_points, alg
     stage = stage_times(fe, views, d_in, 2, False, 3)
     kernel_ms = float((stage[:, 1] + stage[:, 3]).mean())
-    out = {"ms_per_step": ms, "value": n_points / (ms * 1e-3), "unit": UNIT, "steps": steps, "points_per_step": n_points,
-           "scans": scans, "input_gb": n_points * 32 / 1e9, "algorithmic_bytes": alg,
-           "pipeline_frac": alg / (ms * 1e-3) / 1e9 / peak, "kernel_frac": alg / (kernel_ms * 1e-3) / 1e9 / peak,
+    out = {"ms_per_step": ms, "value": n_points_all / (ms * 1e-3), "unit": UNIT, "steps": steps, "points_per_step": n_points_all,
+           "scans": scans * world, "n_gpus": world, "input_gb": n_points_all * 32 / 1e9, "algorithmic_bytes": alg_all,
+           "pipeline_frac": alg_all / (ms * 1e-3) / 1e9 / (peak * world), "kernel_frac": alg / (kernel_ms * 1e-3) / 1e9 / peak,
            "stage_ms": {k: float(stage[:, i].mean()) for i, k in enumerate(STAGES)}, "paths": fe.batch_stats(),
            "selected_fraction": n_feat / max(n_points, 1)}
+    if shard is not None:
+        torch.cuda.synchronize()
+        dist.barrier()              # no peer may still be pushing into this rank's buffers when they are released
+        shard.close()
     fe.close()
     del d_in
     torch.cuda.empty_cache()
@@ -476,7 +508,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters, sharding, synth
+    from lidar_feature_extraction_b200 import FeatureExtraction, PipelinedExtraction, HyperParameters, sharding, synth
     from lidar_feature_extraction_b200 import _native as N
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -686,28 +718,64 @@ def main():
             assert rc == 0, rc
 
         k_e2e = args.e2e_steps or max(2, min(args.steps, 5))
+
+        def timed(step_fn, drain_fn=None):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for k in range(k_e2e):
+                step_fn(k)
+            if drain_fn:
+                drain_fn()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3     # host clock: copies, syncs and both streams are part of the call
+            if world > 1:
+                dist.barrier()
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        # (a) one handle, call by call: upload, kernels and download of a batch in series
         for _ in range(2):
             step_e2e()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(k_e2e):
-            step_e2e()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
-        ms_e2e = max(e0.elapsed_time(e1), wall)  # host-side copies and syncs are part of the call
-        if world > 1:
-            dist.barrier()
-            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
+        ms_serial = timed(lambda k: step_e2e())
         d2h = int(h_counts.nbytes + h_offsets.nbytes + 16 * (int(h_offsets[-1, 0]) + int(h_offsets[-1, 1])))
+
+        # (b) the pipelined host API (PipelinedExtraction = lfx::Pipeline): two handles take the batches in turn, batch
+        #     k-1's features download while batch k uploads on the other stream. Every batch is uploaded, extracted,
+        #     exchanged and downloaded inside the timed region, the last one drained before the clock stops.
+        fe2 = FeatureExtraction(HyperParameters(), device=local_rank, max_rings=max(128, sp.n_rings))
+        shards = (sharded, sharding.AbiShard(fe2, n_frames, rank, world)) if (world > 1 and gather_mode == "abi") else None
+        pipe = PipelinedExtraction(handles=(fe, fe2))
+
+        def pipe_collect():
+            pipe.collect(h_edge, 2 * max(n_feat, 1), h_surf, 2 * max(n_feat, 1))
+
+        def pipe_step(k):
+            slot = pipe.submit(host_views)
+            if shards:
+                shards[slot].exchange()
+            if pipe.in_flight == 2:
+                pipe_collect()
+
+        for k in range(3):
+            pipe_step(k)
+        pipe_collect()
+        ms_e2e = timed(pipe_step, pipe_collect)
+        if shards:
+            shards[1].join()
+            torch.cuda.synchronize()
+            dist.barrier()          # no peer may still be pushing into this rank's buffers when they are released
+            shards[1].close()
         e2e = {"value": n_points * world / (ms_e2e / k_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": d2h, "steps": k_e2e, "ms_per_step": ms_e2e / k_e2e,
+               "api": "PipelinedExtraction (lfx::Pipeline): two handles in turn; all uploads, kernels and downloads of the timed batches inside the timed region",
+               "serial": {"value": n_points * world / (ms_serial / k_e2e * 1e-3), "ms_per_step": ms_serial / k_e2e,
+                          "api": "one handle: lfx_extract_batch then lfx_fetch_counts + lfx_fetch_features, batch by batch"},
                "host_buffers": f"pinned, NUMA node {numa.value} (node of the rank's GPU)" if numa.value >= 0 else "pinned (no NUMA node reported)"}
+        fe2.close()
         lib.lfx_host_free(hptr)
         lib.lfx_host_free(h_edge)
         lib.lfx_host_free(h_surf)
@@ -732,15 +800,21 @@ def main():
 
     # ---- the other BASELINE.json configs and the deployed chain, a few steps each (rank 0, N=1 only)
     workloads = None
-    if rank == 0 and world == 1 and not args.no_workloads:
+    if not args.no_workloads:
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+            if hasattr(sharded, "close"):
+                sharded.close()
         fe.close()
         del d_in
         torch.cuda.empty_cache()
         workloads = {}
         for name in sorted(WORKLOADS):
             if name != args.workload:
-                workloads[name] = measure_workload(name, local_rank, dev, stream, max(5, min(args.steps, 10)), peak)
-        workloads["os128_raw_convert_extract"] = measure_chain(local_rank, dev, stream, max(3, min(args.steps, 5)), peak)
+                workloads[name] = measure_workload(name, local_rank, dev, stream, max(5, min(args.steps, 10)), peak, rank, world)
+        if world == 1:
+            workloads["os128_raw_convert_extract"] = measure_chain(local_rank, dev, stream, max(3, min(args.steps, 5)), peak)
 
     if rank == 0:
         line = {

@@ -340,7 +340,7 @@ int lfx_pose_diff_is_small(const lfx_pose *pose0, const lfx_pose *pose1, double 
 /* Pinned host memory so that H2D/D2H run at full PCIe speed. */
 void *lfx_host_alloc(size_t bytes);
 void lfx_host_free(void *p);
-/* Pinned host memory on the NUMA node of the handle's GPU (sysfs numa_node of its PCI device; set_mempolicy around the
+/* Pinned host memory on the NUMA node of the handle's GPU (sysfs numa_node of its PCI device, else the memory affinity NVML reports; set_mempolicy around the
  * allocation). *numa_node_out (may be NULL): the node the pages were bound to, -1 if the platform gave none. Use it
  * for the scan buffers of a rank that feeds its GPU from host memory; free with lfx_host_free. */
 void *lfx_host_alloc_on(lfx_handle *h, size_t bytes, int *numa_node_out);

@@ -133,6 +133,56 @@ private:
   lfx_handle * h_ = nullptr;
 };
 
+// Offline batches from HOST memory, pipelined: two handles (two streams, two sets of device buffers) take the batches
+// in turn, so that the device-to-host copy of batch k-1's features runs while batch k's host-to-device copy is on the
+// other stream (PCIe is full duplex) and batch k's kernels hide under the upload of batch k+1. Submit(k) enqueues and
+// returns; Collect() hands out the OLDEST batch in flight. Scans are independent (feature_extraction.cpp:92,173-175), so
+// the results equal those of one handle called batch by batch. Input buffers of a batch must stay valid until its Collect.
+class Pipeline
+{
+public:
+  struct Output
+  {
+    std::vector<uint32_t> counts;    // [n_scans][2]
+    std::vector<uint32_t> offsets;   // [n_scans + 1][2]
+    uint32_t n_edge = 0, n_surface = 0;
+  };
+  explicit Pipeline(const HyperParameters & params = HyperParameters(), int device = 0) : fe0_(params, device), fe1_(params, device) {}
+  void Submit(const std::vector<lfx_cloud_view> & scans)
+  {
+    if (in_flight_ == 2) { throw Error(LFX_E_STATE, "two batches in flight: Collect() first"); }
+    n_scans_[head_] = scans.size();
+    handle(head_).ExtractBatch(scans);
+    head_ ^= 1;
+    in_flight_++;
+  }
+  // features into caller memory (pinned for full PCIe speed, lfx_host_alloc_on): capacities in points
+  Output Collect(float * edge_xyz, size_t edge_capacity, float * surface_xyz, size_t surface_capacity)
+  {
+    if (in_flight_ == 0) { throw Error(LFX_E_STATE, "no batch in flight"); }
+    const int slot = in_flight_ == 2 ? head_ : head_ ^ 1;
+    FeatureExtraction & fe = handle(slot);
+    Output out;
+    out.counts.resize(2 * n_scans_[slot]);
+    out.offsets.resize(2 * (n_scans_[slot] + 1));
+    int rc = lfx_fetch_counts(fe.handle(), out.counts.data(), out.offsets.data());
+    if (rc == LFX_OK) { rc = lfx_batch_status(fe.handle()); }
+    if (rc == LFX_OK) { rc = lfx_fetch_features(fe.handle(), edge_xyz, edge_capacity, surface_xyz, surface_capacity); }
+    in_flight_--;
+    if (rc != LFX_OK) { throw Error(rc, lfx_last_error(fe.handle())); }
+    out.n_edge = out.offsets[2 * n_scans_[slot]];
+    out.n_surface = out.offsets[2 * n_scans_[slot] + 1];
+    return out;
+  }
+  int InFlight() const { return in_flight_; }
+  FeatureExtraction & handle(int slot) { return (slot & 1) ? fe1_ : fe0_; }
+
+private:
+  FeatureExtraction fe0_, fe1_;
+  size_t n_scans_[2] = {0, 0};
+  int head_ = 0, in_flight_ = 0;
+};
+
 // fields + point_step of scan_edge / scan_surface / colored_scan (what pcl::toROSMsg derives, ros_msg.hpp:53-71)
 struct TopicLayout
 {

@@ -10,6 +10,7 @@ from .extraction import (  # noqa: F401
     ExtractionError,
     FeatureExtraction,
     HyperParameters,
+    PipelinedExtraction,
     PointCloud2,
     PointField,
     default_params,
@@ -22,7 +23,7 @@ from .localization import LoamProblem  # noqa: F401
 from . import synth  # noqa: F401
 
 __all__ = [
-    "FeatureExtraction", "HyperParameters", "PointCloud2", "PointField", "ExtractionError", "default_params",
+    "FeatureExtraction", "PipelinedExtraction", "HyperParameters", "PointCloud2", "PointField", "ExtractionError", "default_params",
     "launch_yaml_params", "label_to_color", "synth", "POINT_STEP", "PointTypeConverter", "ConvertError", "MapBuilder", "make_pose",
     "pose_diff_is_sufficiently_small", "LoamProblem",
 ]

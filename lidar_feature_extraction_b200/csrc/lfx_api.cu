@@ -983,13 +983,33 @@ static int gpu_numa_node(int device)
 {
   char bus[32] = {0};
   if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
-  for (char * c = bus; *c; c++) { if (*c >= 'A' && *c <= 'F') { *c = (char)(*c - 'A' + 'a'); } }   // sysfs spells it in lower case
-  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
-  FILE * f = fopen(path.c_str(), "r");
-  if (!f) { return -1; }
+  std::string lower(bus);
+  for (char & c : lower) { if (c >= 'A' && c <= 'F') { c = (char)(c - 'A' + 'a'); } }   // sysfs spells it in lower case
+  const std::string path = "/sys/bus/pci/devices/" + lower + "/numa_node";
   int node = -1;
-  if (fscanf(f, "%d", &node) != 1) { node = -1; }
-  fclose(f);
+  if (FILE * f = fopen(path.c_str(), "r")) {
+    if (fscanf(f, "%d", &node) != 1) { node = -1; }
+    fclose(f);
+  }
+  if (node >= 0) { return node; }
+  // Virtual machines often leave sysfs at -1 although the driver knows the node (the "NUMA Affinity" column of
+  // `nvidia-smi topo -m`): ask NVML, loaded at run time so that the library does not link against it.
+  void * so = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_LOCAL);
+  if (!so) { return -1; }
+  using init_fn = int (*)();
+  using by_bus_fn = int (*)(const char *, void **);
+  using affinity_fn = int (*)(void *, unsigned int, unsigned long *, int);
+  auto init = reinterpret_cast<init_fn>(dlsym(so, "nvmlInit_v2"));
+  auto by_bus = reinterpret_cast<by_bus_fn>(dlsym(so, "nvmlDeviceGetHandleByPciBusId_v2"));
+  auto affinity = reinterpret_cast<affinity_fn>(dlsym(so, "nvmlDeviceGetMemoryAffinity"));
+  void * dev = nullptr;
+  unsigned long set[16] = {0};
+  if (init && by_bus && affinity && init() == 0 && by_bus(bus, &dev) == 0 && affinity(dev, 16u, set, 0 /* NVML_AFFINITY_SCOPE_NODE */) == 0) {
+    for (int w = 0; w < 16 && node < 0; w++) {
+      if (set[w]) { node = w * (int)(8 * sizeof(unsigned long)) + __builtin_ctzl(set[w]); }
+    }
+  }
+  // (no nvmlShutdown / dlclose: other users of NVML in the process keep their reference)
   return node;
 }
 

@@ -378,3 +378,74 @@ class FeatureExtraction:
         ms = (C.c_float * 6)()   # LFX_N_STAGES
         self._check(self._lib.lfx_last_stage_ms(self._h, ms))
         return tuple(ms)
+
+
+class PipelinedExtraction:
+    """Offline batches from HOST memory through two handles in turn (mirror of ``lfx::Pipeline``, include/lfx.hpp).
+
+    ``submit(views)`` enqueues a batch on the idle handle and returns; ``collect(...)`` waits for the OLDEST batch in
+    flight and copies its counts and feature clouds to the host. While batch k uploads on one stream, batch k-1's
+    features download on the other (PCIe is full duplex) and batch k's kernels later hide under the upload of batch
+    k+1. Scans are independent (feature_extraction.cpp:92,173-175): results equal one handle called batch by batch.
+    The input buffers of a batch must stay valid until it has been collected.
+    """
+
+    def __init__(self, params: HyperParameters | None = None, device: int = 0, handles=None, **kw):
+        """``handles``: two existing FeatureExtraction objects of the same device to run on (else two are created)."""
+        self._own = handles is None
+        self.fe = tuple(handles) if handles is not None else (FeatureExtraction(params, device, **kw), FeatureExtraction(params, device, **kw))
+        assert len(self.fe) == 2 and self.fe[0] is not self.fe[1]
+        self._head = 0
+        self._in_flight = 0
+        self._n_scans = [0, 0]
+
+    def close(self):
+        if self._own:
+            for fe in self.fe:
+                fe.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def in_flight(self) -> int:
+        return self._in_flight
+
+    def submit(self, views, keep=None) -> int:
+        """Enqueue a batch; returns the slot (0 / 1) of the handle that took it."""
+        if self._in_flight == 2:
+            raise ExtractionError(N.LFX_E_STATE, "two batches in flight: collect() first")
+        arr = views if hasattr(views, "n_views") else FeatureExtraction.view_array(views)
+        slot = self._head
+        self.fe[slot].extract_views(arr, keep=keep)
+        self._n_scans[slot] = arr.n_views
+        self._head ^= 1
+        self._in_flight += 1
+        return slot
+
+    def collect(self, edge_ptr: int = 0, edge_capacity: int = 0, surface_ptr: int = 0, surface_capacity: int = 0):
+        """Counts [n_scans, 2], offsets [n_scans + 1, 2] and, when destination pointers (pinned memory for full PCIe
+        speed, ``lfx_host_alloc_on``) are given, the edge / surface clouds of the oldest batch in flight."""
+        if self._in_flight == 0:
+            raise ExtractionError(N.LFX_E_STATE, "no batch in flight")
+        slot = self._head if self._in_flight == 2 else self._head ^ 1
+        fe, ns = self.fe[slot], self._n_scans[slot]
+        counts = np.zeros((ns, 2), np.uint32)
+        offsets = np.zeros((ns + 1, 2), np.uint32)
+        self._in_flight -= 1
+        fe._check(fe._lib.lfx_fetch_counts(fe.handle, counts.ctypes.data, offsets.ctypes.data))
+        fe._check(fe._lib.lfx_batch_status(fe.handle))
+        if edge_ptr or surface_ptr:
+            fe._check(fe._lib.lfx_fetch_features(fe.handle, edge_ptr or None, edge_capacity, surface_ptr or None, surface_capacity))
+        return counts, offsets
+
+    def collect_output(self) -> BatchOutput:
+        """The oldest batch in flight as a full BatchOutput (numpy arrays; convenience for tests)."""
+        if self._in_flight == 0:
+            raise ExtractionError(N.LFX_E_STATE, "no batch in flight")
+        slot = self._head if self._in_flight == 2 else self._head ^ 1
+        self._in_flight -= 1
+        return self.fe[slot].fetch(fetch_points=True)

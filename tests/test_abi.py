@@ -112,6 +112,7 @@ def test_cpp_host_mirror_compiles_links_and_fails_loudly(tmp_path):
     src.write_text(r'''
 #include <cstdio>
 #include "lfx.hpp"
+struct float4buf { float p[16]; };
 int main() {
   lfx::HyperParameters d;
   lfx::HyperParameters y = lfx::HyperParameters::LaunchYaml();
@@ -126,7 +127,12 @@ int main() {
     lfx::FeatureExtraction fe(d, 0);
     lfx_scan_output out = fe.Extract(v);                                // a GPU is present: one sparse ring, no features
     std::printf("gpu n_edge=%u n_surface=%u\n", out.n_edge, out.n_surface);
-    return (out.n_edge == 0 && out.n_surface == 0) ? 0 : 13;
+    if (out.n_edge != 0 || out.n_surface != 0) { return 13; }
+    lfx::Pipeline pipe(d, 0);                                           // two handles in turn, oldest batch first
+    float4buf e, s;
+    pipe.Submit({v}); pipe.Submit({v, v});
+    const lfx::Pipeline::Output o1 = pipe.Collect(e.p, 4, s.p, 4), o2 = pipe.Collect(e.p, 4, s.p, 4);
+    return (o1.counts.size() == 2 && o2.counts.size() == 4 && o2.n_edge == 0 && pipe.InFlight() == 0) ? 0 : 15;
   } catch (const lfx::Error & e) {
     std::printf("error %d: %s\n", e.code, e.what());
     return e.code == LFX_E_CUDA ? 42 : 14;
