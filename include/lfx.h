@@ -34,7 +34,7 @@ enum {
   LFX_E_NOT_DENSE = 2,  /* feature_extraction.cpp:96-101 */
   LFX_E_NO_RING = 3,    /* feature_extraction.cpp:103-108, RingIsAvailable ring.cpp:36-44 */
   LFX_E_BAD_LAYOUT = 4, /* PointCloud2 view that pcl::fromROSMsg could not map either */
-  LFX_E_CAPACITY = 5,   /* a ring longer than max_ring_points / ring id >= max_rings (see lfx_options) */
+  LFX_E_CAPACITY = 5,   /* ring id >= max_rings (see lfx_options), or an output buffer that is too small */
   LFX_E_CUDA = 6,
   LFX_E_STATE = 7,      /* call order violated (e.g. fetch before extract) */
   LFX_E_CONVERT = 8     /* lfx_convert_batch: at least one cloud failed where the reference converter raises;
@@ -62,7 +62,7 @@ enum {
   LFX_RING_SKIPPED = 2, /* the reference would throw std::invalid_argument and WARN,
                            feature_extraction.cpp:154-156 (too short for the convolution / sectors,
                            or two adjacent points with zero XY norm, math.cpp:40-42) */
-  LFX_RING_TOO_LONG = 3 /* exceeds lfx_options.max_ring_points: reported as LFX_E_CAPACITY */
+  LFX_RING_TOO_LONG = 3 /* transient: a ring above the on-chip capacity before k_extract_rings_big has extracted it */
 };
 
 /* ------------------------------------------------------------------ parameters
@@ -89,7 +89,8 @@ void lfx_launch_yaml_params(lfx_params *out);
 /* Sizing and diagnostics knobs that have no counterpart in the reference. Zero = default. */
 typedef struct lfx_options {
   int device;            /* CUDA device ordinal */
-  int max_ring_points;   /* longest ring held on chip; default 2304, max 8192 */
+  int max_ring_points;   /* longest ring held on chip; default 2304, at most 8192 (larger values are clamped). Longer
+                          * rings are not refused: they run on the unbounded per-ring kernel (lfx_big.cuh) */
   int max_rings;         /* ring ids must be < max_rings; default 128, max 4096 */
   int want_sorted_src;   /* also produce the ring-sorted -> source index map (4 B/point) */
   int want_curvature;    /* also produce per-point curvature, f64 (8 B/point; test/diagnostic mode) */

@@ -27,6 +27,7 @@
 #include "lfx_map.cuh"
 #include "lfx_shard.cuh"
 #include "lfx_loc.cuh"
+#include "lfx_big.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is loaded at run time (lfx_shard_*), single-GPU users do not need it
@@ -69,7 +70,8 @@ struct lfx_handle
   DevParams dev{};
   int device = 0;
   int num_sms = 0;
-  int ring_grid = 0, pack_grid = 0;
+  int ring_grid = 0, pack_grid = 0, big_grid = 0;
+  bool ring_enabled = true;   // the on-chip per-ring kernel covers these parameters (else every ring takes k_extract_rings_big)
   int tile = TILE_SMALL;   // points per ingest tile (TILE_BIG when the scatter's shared memory fits)
   size_t ring_smem = 0;
   int cap = 0;
@@ -281,8 +283,9 @@ int validate_params(const lfx_params & p, std::string & why)
     why = "all nine parameters must be > 0 (hyper_parameter.hpp:45-53)";
     return LFX_E_BAD_PARAM;
   }
-  if (p.padding > MAX_PADDING) { why = "convolution_padding > 15 is outside the supported envelope"; return LFX_E_BAD_PARAM; }
-  if (p.n_blocks > MAX_BLOCKS) { why = "n_blocks > 64 is outside the supported envelope"; return LFX_E_BAD_PARAM; }
+  // no upper bounds, like the reference: paddings above MAX_PADDING and more than MAX_BLOCKS sectors run on
+  // k_extract_rings_big (lfx_big.cuh); only the arithmetic on positions has to stay inside 32 bits
+  if (p.padding > (1 << 24) || p.n_blocks > (1 << 24)) { why = "convolution_padding / n_blocks above 2^24"; return LFX_E_BAD_PARAM; }
   return LFX_OK;
 }
 
@@ -343,7 +346,8 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
       h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_ring16.p, h->d_tile_hist.p, max_rings, h->d_counters);
   }
   k_ring_plan<<<n_scans, 256, sizeof(uint32_t) * 2 * max_rings, h->stream>>>(
-    h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, max_rings, h->params.padding, h->cap);
+    h->d_scans.p, h->d_scan_flags.p, h->d_tile_hist.p, h->d_rings.p, h->d_ring_src.p, max_rings, h->params.padding,
+    h->ring_enabled ? h->cap : 0);   // longer rings are marked LFX_RING_TOO_LONG: the big kernel's share
   if (h->tile == TILE_BIG) {
     k_ring_scatter<TILE_BIG><<<ingest_grid, INGEST_THREADS, scatter_smem_bytes(max_rings, TILE_BIG), h->stream>>>(
       h->d_scans.p, h->d_gen_scan.p, h->d_gen_tile_base.p, h->d_tile_owner.p, h->d_counters, h->d_ring16.p, h->d_tile_hist.p, h->d_rings.p, h->d_idx.p, max_rings);
@@ -407,7 +411,24 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   ra.cap = h->cap;
   ra.force_order_path = h->opt.force_order_path;
   ra.prm = h->dev;
-  h->ring_kernel<<<h->ring_grid, h->ring_threads, h->ring_smem, h->stream>>>(ra);
+  if (h->ring_enabled) { h->ring_kernel<<<h->ring_grid, h->ring_threads, h->ring_smem, h->stream>>>(ra); }
+  {
+    BigArgs ba;
+    ba.scans = h->d_scans.p;
+    ba.idx = h->d_idx.p;
+    ba.rings = h->d_rings.p;
+    ba.work = h->d_work.p;
+    ba.counters = h->d_counters;
+    ba.labels = h->d_labels.p;
+    ba.sorted_src = ra.sorted_src;
+    ba.curvature = ra.curvature;
+    ba.stage = h->d_stage.p;
+    ba.tmp16 = h->d_ring16.p;
+    ba.max_rings = max_rings;
+    ba.all = h->ring_enabled ? 0 : 1;
+    ba.prm = h->dev;
+    k_extract_rings_big<<<h->big_grid, BIG_THREADS, 0, h->stream>>>(ba);
+  }
   if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[5], h->stream, ev_flags)); }
   // ---- packing
   k_feat_offsets_a<<<n_scans, 128, 0, h->stream>>>(h->d_rings.p, h->d_ring_featoff.p, h->d_counts.p, max_rings);
@@ -435,7 +456,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   return LFX_OK;
 }
 
-int kernels_per_batch(const lfx_handle * h) { return h->fast_enabled ? 11 + 2 * N_FAST_K + 1 : 11; }
+int kernels_per_batch(const lfx_handle * h) { return (h->fast_enabled ? 11 + 2 * N_FAST_K + 1 : 11) + (h->ring_enabled ? 1 : 0); }
 
 }  // namespace
 
@@ -485,13 +506,17 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   if (options) { h->opt = *options; }
   if (h->opt.max_ring_points <= 0) { h->opt.max_ring_points = 2304; }
   if (h->opt.max_rings <= 0) { h->opt.max_rings = 128; }
-  if (h->opt.max_ring_points > 8192 || h->opt.max_rings > 4096 || h->opt.force_order_path < 0 || h->opt.force_order_path > 2) {
-    g_create_error = "lfx_options outside the supported envelope (max_ring_points <= 8192, max_rings <= 4096)";
+  if (h->opt.max_rings > 4096 || h->opt.force_order_path < 0 || h->opt.force_order_path > 2) {
+    g_create_error = "lfx_options outside the supported envelope (max_rings <= 4096)";
     delete h;
     return LFX_E_BAD_PARAM;
   }
   h->device = h->opt.device;
-  h->cap = (std::max(h->opt.max_ring_points, 2 * params->padding + 2) + 255) & ~255;
+  // The on-chip per-ring kernel holds rings of up to `cap` points (at most 8192: 1024 threads x 8 positions) and is
+  // compiled for paddings <= MAX_PADDING and <= MAX_BLOCKS sectors; whatever lies beyond runs on k_extract_rings_big.
+  h->ring_enabled = params->padding <= MAX_PADDING && params->n_blocks <= MAX_BLOCKS;
+  h->opt.max_ring_points = std::min(h->opt.max_ring_points, 8192);
+  h->cap = (std::max(h->opt.max_ring_points, h->ring_enabled ? 2 * params->padding + 2 : 0) + 255) & ~255;
   h->ring_threads = h->cap / PTS;
 
   auto bail = [&](cudaError_t e, const char * what) {
@@ -534,15 +559,23 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   h->dev.center_w = -2. * params->padding;  // MakeWeight curvature.cpp:40
 
   // kernel attributes / persistent grid sizes
-  h->ring_smem = ring_smem_bytes(h->cap, params->padding);
-  if (h->ring_smem > (size_t)prop.sharedMemPerBlockOptin) {
-    g_create_error = "max_ring_points does not fit in shared memory";
-    lfx_destroy(h);
-    return LFX_E_BAD_PARAM;
+  int occ = 0;
+  if (h->ring_enabled) {
+    // (a capacity that does not fit the shared memory of this device is lowered: longer rings take the big kernel)
+    while (h->cap > 256 && ring_smem_bytes(h->cap, params->padding) > (size_t)prop.sharedMemPerBlockOptin) { h->cap -= 256; }
+    h->ring_threads = h->cap / PTS;
+    h->ring_smem = ring_smem_bytes(h->cap, params->padding);
+    if (h->ring_smem > (size_t)prop.sharedMemPerBlockOptin) { h->ring_enabled = false; }
   }
-  int tmax = 0;
-  h->ring_kernel = pick_ring_kernel(params->padding, h->ring_threads, &tmax);
-  if ((e = cudaFuncSetAttribute(h->ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ring_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(rings)"); }
+  if (h->ring_enabled) {
+    int tmax = 0;
+    h->ring_kernel = pick_ring_kernel(params->padding, h->ring_threads, &tmax);
+    if ((e = cudaFuncSetAttribute(h->ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->ring_smem)) != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(rings)"); }
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->ring_kernel, h->ring_threads, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
+    h->ring_grid = h->num_sms * std::max(occ, 1);
+  }
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extract_rings_big, BIG_THREADS, 0)) != cudaSuccess) { return bail(e, "occupancy(big rings)"); }
+  h->big_grid = h->num_sms * std::max(occ, 1);
   // ingest tile: the big one while three scatter CTAs still fit an SM
   h->tile = scatter_smem_bytes(h->opt.max_rings, TILE_BIG) * 3 <= (size_t)prop.sharedMemPerMultiprocessor ? TILE_BIG : TILE_SMALL;
   const size_t scatter_smem = scatter_smem_bytes(h->opt.max_rings, h->tile);
@@ -551,9 +584,6 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
                             : cudaFuncSetAttribute(k_ring_scatter<TILE_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
     if (e != cudaSuccess) { return bail(e, "cudaFuncSetAttribute(scatter)"); }
   }
-  int occ = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->ring_kernel, h->ring_threads, h->ring_smem)) != cudaSuccess) { return bail(e, "occupancy(rings)"); }
-  h->ring_grid = h->num_sms * std::max(occ, 1);
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack_copy, 256, 0)) != cudaSuccess) { return bail(e, "occupancy(pack)"); }
   h->pack_grid = h->num_sms * std::max(occ, 1);
   h->ingest_grid = h->num_sms * 8;

@@ -334,15 +334,15 @@ k_extract_rings(const RingArgs a)
     const uint64_t pos0 = meta.sd.point_base + meta.info.offset;
     const uint32_t status_in = meta.info.status;
 
-    // ---- rings that contribute nothing: sparse (ring.cpp:46-59) or over capacity
+    // ---- rings that contribute nothing: sparse (ring.cpp:46-59). Rings over this kernel's capacity are left to
+    //      k_extract_rings_big (lfx_big.cuh), which runs after it over the same work list.
     if (status_in != LFX_RING_OK) {
-      for (int i = tid; i < n; i += T) {
-        a.labels[pos0 + i] = LFX_LABEL_NONE;
-        if (a.sorted_src) { a.sorted_src[pos0 + i] = src_index(a, meta, pos0, i); }
-        if (a.curvature) { a.curvature[pos0 + i] = 0.0; }
-      }
-      if (status_in == LFX_RING_TOO_LONG && tid == 0) {
-        if (atomicExch(&a.counters[C_ERR_FLAG], LFX_E_CAPACITY) == 0) { a.counters[C_ERR_SCAN] = item.x; a.counters[C_ERR_RING] = item.y; }
+      if (status_in != LFX_RING_TOO_LONG) {
+        for (int i = tid; i < n; i += T) {
+          a.labels[pos0 + i] = LFX_LABEL_NONE;
+          if (a.sorted_src) { a.sorted_src[pos0 + i] = src_index(a, meta, pos0, i); }
+          if (a.curvature) { a.curvature[pos0 + i] = 0.0; }
+        }
       }
       __syncthreads();
       continue;

@@ -1,0 +1,84 @@
+"""The reference has no upper bound on ring length, convolution_padding or n_blocks (hyper_parameter.hpp:45-53 asserts
+"> 0" only, index_range.cpp:32-66). Whatever the two on-chip kernels do not hold runs on k_extract_rings_big
+(lfx_big.cuh) and must come out exactly as the oracle has it (the oracle is pinned to the compiled reference for these
+parameter sets in tests/test_oracle_vs_ref.py)."""
+import numpy as np
+import pytest
+
+import adversarial as adv
+from helpers import compare_scan, oracle_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _fe(hp=None, **kw):
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters
+
+    kw.setdefault("want_sorted_src", True)
+    kw.setdefault("want_curvature", True)
+    return FeatureExtraction(hp or HyperParameters(), device=0, **kw)
+
+
+def _hp(**kw):
+    from lidar_feature_extraction_b200 import HyperParameters
+
+    return HyperParameters(**kw)
+
+
+def _check(oracle, hp, clouds, **kw):
+    from oracle import binding as ob
+
+    with _fe(hp, **kw) as fe:
+        out = fe.extract_batch(clouds)
+        stats = fe.batch_stats()
+    for s, cloud in enumerate(clouds):
+        compare_scan(out, s, cloud, oracle.extract_scan(cloud, oracle_params(ob, hp)))
+    return out, stats
+
+
+@pytest.mark.parametrize("shuffle", ["none", "interleave", "random", "rotate", "rotate_reverse", "reverse"])
+def test_rings_longer_than_the_on_chip_capacity(oracle, shuffle):
+    """Rings above lfx_options.max_ring_points (here 256) and above the hard 8192 of the on-chip kernel."""
+    clouds = [adv.ragged_scan(3, [100, 400, 3, 0, 1500], shuffle=shuffle),
+              adv.ragged_scan(4, [10000, 300, 9001], shuffle=shuffle, zero_xy=1)]
+    _check(oracle, _hp(), clouds[:1], max_ring_points=256)
+    _check(oracle, _hp(), clouds)
+    _check(oracle, _hp(padding=2, neighbor_degree_threshold=3.0, edge_threshold=50.0, max_range=1000.0), clouds)
+
+
+@pytest.mark.parametrize("kind", ["ramp", "plateau", "gaps", "steps", "spiky"])
+def test_long_rings_of_every_kind(oracle, kind):
+    """Selection depth (ramp), exact ties (plateau), broken links (gaps), occlusion (steps) on rings of 9000+ points."""
+    clouds = [adv.ragged_scan(7, [9000, 12000], kinds=[kind], shuffle="interleave")]
+    _check(oracle, _hp(), clouds)
+    _check(oracle, _hp(n_blocks=1), clouds)
+
+
+PARAMSETS = {
+    "p20": dict(padding=20),
+    "p40b3": dict(padding=40, n_blocks=3, edge_threshold=0.5, surface_threshold=0.5),
+    "b100": dict(n_blocks=100),
+    "p1b300": dict(padding=1, n_blocks=300, neighbor_degree_threshold=5.0),
+    "p33b70": dict(padding=33, n_blocks=70),
+}
+
+
+@pytest.mark.parametrize("pname", sorted(PARAMSETS))
+@pytest.mark.parametrize("shuffle", ["none", "interleave", "random", "rotate_reverse"])
+def test_parameters_beyond_the_compiled_envelope(oracle, pname, shuffle):
+    hp = _hp(**PARAMSETS[pname])
+    clouds = []
+    for seed in range(4):
+        rng = np.random.default_rng(300 + seed)
+        lengths = [int(v) for v in rng.choice([0, 1, 6, 23, 40, 67, 97, 300, 777, 2048, 2500], size=8)]
+        clouds.append(adv.ragged_scan(seed, lengths, shuffle=shuffle, zero_xy=seed % 3))
+    _check(oracle, hp, clouds)
+
+
+def test_sensor_shaped_scans_with_a_long_window(oracle):
+    """A regular scan under padding 20: the sector kernel is not compiled for it, every ring takes the big kernel."""
+    from lidar_feature_extraction_b200 import synth
+
+    clouds = [synth.scan_host(synth.spec("vlp16"), f) for f in range(2)]
+    _, stats = _check(oracle, _hp(padding=20), clouds)
+    assert stats["fast_rings"] == [0, 0, 0] and stats["general_scans"] == 2

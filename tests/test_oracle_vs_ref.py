@@ -32,6 +32,11 @@ PARAMSETS = {
     "yaml": ob.launch_yaml_params(),
     "p2b4": ob.default_params(padding=2, n_blocks=4, edge_threshold=0.02, surface_threshold=0.2),
     "p8b3": ob.default_params(padding=8, n_blocks=3, neighbor_degree_threshold=1.0),
+    # beyond what the on-chip CUDA kernels are compiled for (k_extract_rings_big, tests/test_gpu_envelope.py)
+    "p20": ob.default_params(padding=20),
+    "p40b3": ob.default_params(padding=40, n_blocks=3, edge_threshold=0.5, surface_threshold=0.5),
+    "b100": ob.default_params(n_blocks=100),
+    "p33b70": ob.default_params(padding=33, n_blocks=70),
 }
 
 
@@ -54,6 +59,14 @@ def test_adversarial(oracle, reference_stable, pname, shuffle):
         rng = np.random.default_rng(100 + seed)
         lengths = [int(v) for v in rng.choice([0, 1, 3, 6, 11, 12, 17, 23, 40, 97, 300, 777], size=7)]
         cloud = adv.ragged_scan(seed, lengths, shuffle=shuffle, zero_xy=seed % 3)
+        same(oracle.extract_scan(cloud, prm), reference_stable.extract_scan(cloud, prm))
+
+
+@pytest.mark.parametrize("shuffle", ["interleave", "random"])
+def test_long_rings(oracle, reference_stable, shuffle):
+    """Rings beyond the on-chip capacity of the CUDA kernels (8192 points)."""
+    for prm in (PARAMSETS["default"], PARAMSETS["yaml"]):
+        cloud = adv.ragged_scan(4, [10000, 300, 9001], shuffle=shuffle, zero_xy=1)
         same(oracle.extract_scan(cloud, prm), reference_stable.extract_scan(cloud, prm))
 
 
