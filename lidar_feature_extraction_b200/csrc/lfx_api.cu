@@ -29,6 +29,17 @@
 #include "lfx_loc.cuh"
 #include "lfx_big.cuh"
 
+namespace lfxk
+{
+// lfx_sector_extra.cu, one translation unit per padding
+void sector_kernels_p1(bool diag, void (**out)(const SectorArgs));
+void sector_kernels_p3(bool diag, void (**out)(const SectorArgs));
+void sector_kernels_p4(bool diag, void (**out)(const SectorArgs));
+void sector_kernels_p6(bool diag, void (**out)(const SectorArgs));
+void sector_kernels_p7(bool diag, void (**out)(const SectorArgs));
+void sector_kernels_p8(bool diag, void (**out)(const SectorArgs));
+}  // namespace lfxk
+
 #include <dlfcn.h>
 #include <nccl.h>      // types only: the library is loaded at run time (lfx_shard_*), single-GPU users do not need it
 #include <sys/syscall.h>
@@ -265,12 +276,24 @@ void pick_sector_kernels_t(void (**out)(const SectorArgs))
   out[5] = k_extract_sectors<P, fast_k(2), DIAG, true>;
 }
 
-// The sector kernel is compiled for the two deployed paddings (compiled default 5, launch YAML 2);
-// any other padding runs on the general ring kernel only.
+// The sector kernel is compiled for convolution_padding 1..8: the two deployed paddings (compiled default 5, launch
+// YAML 2) here, the others in their own translation units (lfx_sector_extra.cu); any other padding runs on the per-ring
+// kernels only.
 bool pick_sector_kernels(int padding, bool diag, void (**out)(const SectorArgs))
 {
   if (padding == 5) { if (diag) { pick_sector_kernels_t<5, true>(out); } else { pick_sector_kernels_t<5, false>(out); } return true; }
   if (padding == 2) { if (diag) { pick_sector_kernels_t<2, true>(out); } else { pick_sector_kernels_t<2, false>(out); } return true; }
+#ifdef LFX_EXTRA_PADDINGS
+  switch (padding) {
+    case 1: lfxk::sector_kernels_p1(diag, out); return true;
+    case 3: lfxk::sector_kernels_p3(diag, out); return true;
+    case 4: lfxk::sector_kernels_p4(diag, out); return true;
+    case 6: lfxk::sector_kernels_p6(diag, out); return true;
+    case 7: lfxk::sector_kernels_p7(diag, out); return true;
+    case 8: lfxk::sector_kernels_p8(diag, out); return true;
+    default: break;
+  }
+#endif
   return false;
 }
 

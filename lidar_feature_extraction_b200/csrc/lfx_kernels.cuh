@@ -154,7 +154,7 @@ __device__ __forceinline__ int find_gen_scan(const uint32_t * gen_tile_base, int
 }
 
 // single CTA: list of flagged scans + exclusive prefix of their tile counts
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t * __restrict__ scan_flags,
                uint32_t * __restrict__ gen_scan, uint32_t * __restrict__ gen_tile_base, uint32_t * __restrict__ tile_owner,
                uint32_t * counters)
@@ -263,7 +263,7 @@ k_ring_hist(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ g
 
 // ------------------------------------------------------------------ ingest: plan (one CTA per scan)
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ scan_flags, uint32_t * __restrict__ tile_hist,
             lfx_ring_info * __restrict__ rings, uint2 * __restrict__ ring_src, int max_rings, int padding, int cap)
 {
@@ -450,7 +450,7 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
 // ------------------------------------------------------------------ packing
 
 // per scan: exclusive prefix of (n_edge, n_surface) over rings ascending -> ring_featoff, totals -> counts
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 k_feat_offsets_a(const lfx_ring_info * __restrict__ rings, uint2 * __restrict__ ring_featoff,
                  uint32_t * __restrict__ counts, int max_rings)
 {
@@ -478,7 +478,7 @@ k_feat_offsets_a(const lfx_ring_info * __restrict__ rings, uint2 * __restrict__ 
 }
 
 // single CTA: exclusive prefix over scans -> offsets[(n_scans+1)][2]
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 k_feat_offsets_b(const uint32_t * __restrict__ counts, uint32_t * __restrict__ offsets, int n_scans)
 {
   __shared__ uint32_t s_e[1024], s_s[1024];
@@ -505,7 +505,7 @@ k_feat_offsets_b(const uint32_t * __restrict__ counts, uint32_t * __restrict__ o
 }
 
 // persistent: one work item (scan, ring) per CTA iteration; staged -> final concatenated clouds
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_pack_copy(const uint2 * __restrict__ work, uint32_t * counters, const ScanDesc * __restrict__ scans,
             const lfx_ring_info * __restrict__ rings, const uint2 * __restrict__ ring_featoff,
             const uint32_t * __restrict__ offsets, const float4 * __restrict__ stage,

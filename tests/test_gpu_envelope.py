@@ -82,3 +82,19 @@ def test_sensor_shaped_scans_with_a_long_window(oracle):
     clouds = [synth.scan_host(synth.spec("vlp16"), f) for f in range(2)]
     _, stats = _check(oracle, _hp(padding=20), clouds)
     assert stats["fast_rings"] == [0, 0, 0] and stats["general_scans"] == 2
+
+
+@pytest.mark.parametrize("padding", [1, 3, 4, 6, 7, 8])
+@pytest.mark.parametrize("sensor", ["vlp16", "hdl64", "os128"])
+def test_every_padding_up_to_eight_runs_on_the_sector_kernel(oracle, padding, sensor):
+    """convolution_padding 1..8 are compiled instantiations of k_extract_sectors (5 and 2 in lfx_api.cu, the others in
+    lfx_sector_extra.cu): regular scans take the strided sector path, drop-out scans (hdl64) the indexed one; no ring
+    is left to the per-ring kernels."""
+    from lidar_feature_extraction_b200 import synth
+
+    clouds = [synth.scan_host(synth.spec(sensor), f) for f in range(2)]
+    _, stats = _check(oracle, _hp(padding=padding), clouds)
+    assert stats["general_rings"] == 0, stats
+    assert sum(stats["fast_rings"]) + sum(stats["indexed_rings"]) == 2 * synth.spec(sensor).n_rings, stats
+    if sensor != "hdl64":
+        assert stats["general_scans"] == 0, stats

@@ -200,9 +200,12 @@ def test_mixed_batches(oracle):
 
 
 def test_other_paddings_use_the_general_kernel(oracle):
+    """The sector kernel is compiled for convolution_padding 1..8 (tests/test_gpu_envelope.py); 9..15 run on the on-chip
+    per-ring kernel with run-time loops."""
     clouds = [regular_scan(3, 4, 900)]
-    out, stats = _check(oracle, _hp(padding=3), clouds)
-    assert sum(stats["fast_rings"]) == 0 and stats["general_scans"] == 1
+    for padding in (9, 12):
+        out, stats = _check(oracle, _hp(padding=padding), clouds)
+        assert sum(stats["fast_rings"]) == 0 and stats["general_scans"] == 1
 
 
 def test_full_size_batch_properties(oracle):

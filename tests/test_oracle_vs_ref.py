@@ -62,6 +62,16 @@ def test_adversarial(oracle, reference_stable, pname, shuffle):
         same(oracle.extract_scan(cloud, prm), reference_stable.extract_scan(cloud, prm))
 
 
+@pytest.mark.parametrize("padding", [1, 3, 4, 6, 7, 8])
+def test_every_padding_of_the_sector_kernel(oracle, reference_stable, padding):
+    from lidar_feature_extraction_b200 import synth
+
+    prm = ob.default_params(padding=padding)
+    for sensor in ("vlp16", "hdl64"):
+        cloud = synth.scan_host(synth.spec(sensor), 1)
+        same(oracle.extract_scan(cloud, prm), reference_stable.extract_scan(cloud, prm))
+
+
 @pytest.mark.parametrize("shuffle", ["interleave", "random"])
 def test_long_rings(oracle, reference_stable, shuffle):
     """Rings beyond the on-chip capacity of the CUDA kernels (8192 points)."""
