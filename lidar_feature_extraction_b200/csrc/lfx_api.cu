@@ -2122,7 +2122,17 @@ void lfx_shard_destroy(lfx_shard * s)
 
 // ====================================================================== localization residual build
 
-struct LocMap { double * x = nullptr, * y = nullptr, * z = nullptr; uint64_t n = 0, cap = 0; };
+struct LocMap
+{
+  double * x = nullptr, * y = nullptr, * z = nullptr;   // map order (what the neighbour indices address)
+  uint64_t n = 0, cap = 0;
+  // uniform grid over the map (k_loc_knn_grid): the same points cell by cell + their map indices
+  double * gx = nullptr, * gy = nullptr, * gz = nullptr;
+  uint32_t * gidx = nullptr, * cell_start = nullptr, * cell_count = nullptr;
+  uint64_t cells_cap = 0;
+  lfxk::LocGrid grid{};
+  bool use_grid = false;
+};
 
 struct LocState
 {
@@ -2160,7 +2170,71 @@ template<int K>
 void launch_knn(lfx_handle * h, const LocMap & m, const float4 * scan, uint32_t n, const lfxk::LocPose & T, uint32_t * nbr, double * d2)
 {
   const unsigned grid = (n + lfxk::LOC_KNN_WARPS - 1) / lfxk::LOC_KNN_WARPS;
-  lfxk::k_loc_knn<K><<<grid, lfxk::LOC_KNN_WARPS * 32, 0, h->stream>>>(m.x, m.y, m.z, (uint32_t)m.n, scan, n, T, nbr, d2);
+  if (m.use_grid) { lfxk::k_loc_knn_grid<K><<<grid, lfxk::LOC_KNN_WARPS * 32, 0, h->stream>>>(m.grid, scan, n, T, nbr, d2); }
+  else { lfxk::k_loc_knn<K><<<grid, lfxk::LOC_KNN_WARPS * 32, 0, h->stream>>>(m.x, m.y, m.z, (uint32_t)m.n, scan, n, T, nbr, d2); }
+}
+
+float loc_unkey(uint32_t k) { const uint32_t b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k; float f; memcpy(&f, &b, 4); return f; }
+
+// uniform grid over the map for k_loc_knn_grid (see lfx_loc.cuh); src: the map as float4 on the device
+int loc_build_grid(lfx_handle * h, LocMap & m, const float4 * src)
+{
+  const char * ex = getenv("LFX_LOC_EXHAUSTIVE");   // diagnosis: answer by exhaustive search (k_loc_knn)
+  m.use_grid = false;
+  if (ex && atoi(ex) != 0) { return LFX_OK; }
+  if (m.n > 0xFFFFFFF0ull) { return LFX_OK; }       // (refused later: 32-bit neighbour indices)
+  uint32_t * d_keys = nullptr, h_keys[6];
+  LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&d_keys), sizeof(h_keys)));
+  cudaMemsetAsync(d_keys, 0xFF, 3 * sizeof(uint32_t), h->stream);
+  cudaMemsetAsync(d_keys + 3, 0, 3 * sizeof(uint32_t), h->stream);
+  lfxk::k_loc_bbox<<<h->num_sms * 4, 256, 0, h->stream>>>(src, m.n, d_keys);
+  cudaMemcpyAsync(h_keys, d_keys, sizeof(h_keys), cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_keys);
+  LFX_CUDA(h, e);
+  lfxk::LocGrid g{};
+  double ext[3] = {0, 0, 0};
+  double lo[3] = {0, 0, 0};
+  for (int a = 0; a < 3; a++) {
+    if (h_keys[a] <= h_keys[3 + a]) { lo[a] = (double)loc_unkey(h_keys[a]); ext[a] = (double)loc_unkey(h_keys[3 + a]) - lo[a]; }
+  }
+  const char * cs = getenv("LFX_LOC_CELL");
+  double c = cs && atof(cs) > 0 ? atof(cs) : 1.0;   // metres: LOAM maps are voxel-filtered to a few points per cell of this size
+  uint64_t dims[3];
+  for (;;) {
+    uint64_t cells = 1;
+    bool fits = true;
+    for (int a = 0; a < 3; a++) {
+      const double d = std::floor(ext[a] / c) + 1.0;
+      if (!(d < 4.0e9)) { fits = false; break; }
+      dims[a] = (uint64_t)d;
+      cells *= dims[a];
+      if (cells > lfxk::LOC_MAX_CELLS) { fits = false; break; }
+    }
+    if (fits) { break; }
+    c *= 1.2599210498948732;   // 2^(1/3): half as many cells
+  }
+  g.x0 = lo[0]; g.y0 = lo[1]; g.z0 = lo[2];
+  g.c = c; g.inv_c = 1.0 / c;
+  g.nx = (int)dims[0]; g.ny = (int)dims[1]; g.nz = (int)dims[2];
+  const uint64_t n_cells = dims[0] * dims[1] * dims[2];
+  if (n_cells + 1 > m.cells_cap) {
+    cudaFree(m.cell_start); cudaFree(m.cell_count);
+    m.cell_start = m.cell_count = nullptr; m.cells_cap = 0;
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.cell_start), sizeof(uint32_t) * (n_cells + 1)));
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.cell_count), sizeof(uint32_t) * (n_cells + 1)));
+    m.cells_cap = n_cells + 1;
+  }
+  g.cell_start = m.cell_start; g.gx = m.gx; g.gy = m.gy; g.gz = m.gz; g.gidx = m.gidx;
+  LFX_CUDA(h, cudaMemsetAsync(m.cell_count, 0, sizeof(uint32_t) * n_cells, h->stream));
+  lfxk::k_loc_cell_count<<<h->num_sms * 4, 256, 0, h->stream>>>(m.x, m.y, m.z, m.n, g, m.cell_count);
+  lfxk::k_loc_cell_scan<<<1, 1024, 0, h->stream>>>(m.cell_count, m.cell_start, (uint32_t)n_cells);
+  lfxk::k_loc_cell_fill<<<h->num_sms * 4, 256, 0, h->stream>>>(m.x, m.y, m.z, m.n, g, m.cell_count, m.gx, m.gy, m.gz, m.gidx);
+  LFX_CUDA(h, cudaGetLastError());
+  h->launches += 4;
+  m.grid = g;
+  m.use_grid = true;
+  return LFX_OK;
 }
 
 int loc_run(lfx_handle * h, int kind, const float * scan_xyz4, uint32_t n, int memory, const lfx_pose * pose, int k, double * J_out,
@@ -2218,14 +2292,19 @@ int lfx_loc_set_map(lfx_handle * h, int kind, const float * xyz4, uint64_t n, in
   LocMap & m = st.map[kind];
   if (n > m.cap) {
     LFX_CUDA(h, cudaStreamSynchronize(h->stream));
-    cudaFree(m.x); cudaFree(m.y); cudaFree(m.z);
-    m.x = m.y = m.z = nullptr; m.cap = 0;
+    cudaFree(m.x); cudaFree(m.y); cudaFree(m.z); cudaFree(m.gx); cudaFree(m.gy); cudaFree(m.gz); cudaFree(m.gidx);
+    m.x = m.y = m.z = m.gx = m.gy = m.gz = nullptr; m.gidx = nullptr; m.cap = 0;
     LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.x), sizeof(double) * n));
     LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.y), sizeof(double) * n));
     LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.z), sizeof(double) * n));
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.gx), sizeof(double) * n));
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.gy), sizeof(double) * n));
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.gz), sizeof(double) * n));
+    LFX_CUDA(h, cudaMalloc(reinterpret_cast<void **>(&m.gidx), sizeof(uint32_t) * n));
     m.cap = n;
   }
   m.n = n;
+  m.use_grid = false;
   if (n == 0) { return LFX_OK; }
   const float4 * src = reinterpret_cast<const float4 *>(xyz4);
   float4 * tmp = nullptr;
@@ -2237,8 +2316,11 @@ int lfx_loc_set_map(lfx_handle * h, int kind, const float * xyz4, uint64_t n, in
   lfxk::k_loc_soa<<<h->num_sms * 4, 256, 0, h->stream>>>(src, n, m.x, m.y, m.z);
   LFX_CUDA(h, cudaGetLastError());
   h->launches += 1;
-  LFX_CUDA(h, cudaStreamSynchronize(h->stream));
+  const int grc = loc_build_grid(h, m, src);
+  cudaError_t se = cudaStreamSynchronize(h->stream);
   if (tmp) { cudaFree(tmp); }
+  if (grc != LFX_OK) { return grc; }
+  LFX_CUDA(h, se);
   return LFX_OK;
 }
 
@@ -2261,7 +2343,7 @@ int lfx_loc_release(lfx_handle * h)
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); }
   LocState & st = *h->loc;
-  for (LocMap & m : st.map) { cudaFree(m.x); cudaFree(m.y); cudaFree(m.z); }
+  for (LocMap & m : st.map) { cudaFree(m.x); cudaFree(m.y); cudaFree(m.z); cudaFree(m.gx); cudaFree(m.gy); cudaFree(m.gz); cudaFree(m.gidx); cudaFree(m.cell_start); cudaFree(m.cell_count); }
   cudaFree(st.d_scan.p); cudaFree(st.d_nbr.p); cudaFree(st.d_d2.p); cudaFree(st.d_J.p); cudaFree(st.d_r.p);
   delete h->loc;
   h->loc = nullptr;

@@ -116,6 +116,202 @@ k_loc_knn(const double * __restrict__ mx, const double * __restrict__ my, const 
   }
 }
 
+// ---- exact k nearest neighbours through a uniform grid over the map (built once per lfx_loc_set_map)
+//
+// The map's points are bucketed into cubic cells (edge c >= 1 m, enlarged until the bounding box holds at most
+// LOC_MAX_CELLS of them) and stored cell by cell (x fastest), so a row of cells along x is ONE contiguous range of points.
+// A warp answers one query: it visits the cells around the query shell by shell (Chebyshev radius s = 0, 1, 2, ...),
+// every lane keeping the k best of the points it saw, and stops as soon as k visited points are strictly closer than
+// anything outside the visited cube can be - the distance from the query to the nearest face of the cube that still has
+// cells behind it, less a safety margin that dwarfs the rounding of the cell assignment. The k best are then exactly
+// those of the exhaustive search: same metric (nanoflann's L2 over doubles), same (distance, index) order.
+constexpr uint32_t LOC_MAX_CELLS = 1u << 22;
+
+struct LocGrid
+{
+  double x0, y0, z0;      // lower corner
+  double c, inv_c;        // cell edge
+  int nx, ny, nz;
+  const uint32_t * cell_start;   // [nx * ny * nz + 1]
+  const double * gx, * gy, * gz; // the map's points, cell by cell
+  const uint32_t * gidx;         // their indices in the map
+};
+
+__device__ __forceinline__ int loc_cell1(double v, double v0, double inv_c, int n)
+{
+  const double t = floor((v - v0) * inv_c);
+  return (int)fmin(fmax(t, 0.0), (double)(n - 1));   // (NaN -> 0)
+}
+__device__ __forceinline__ uint32_t loc_cell(const LocGrid & g, double x, double y, double z)
+{
+  const int cx = loc_cell1(x, g.x0, g.inv_c, g.nx), cy = loc_cell1(y, g.y0, g.inv_c, g.ny), cz = loc_cell1(z, g.z0, g.inv_c, g.nz);
+  return ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+}
+
+// float -> unsigned key with the same order
+__device__ __forceinline__ uint32_t loc_fkey(float f) { const uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
+
+// bounding box of the finite points: keys[0..2] = min x,y,z, keys[3..5] = max x,y,z (initialised to ~0 / 0)
+__global__ void __launch_bounds__(256)
+k_loc_bbox(const float4 * __restrict__ pts, uint64_t n, uint32_t * __restrict__ keys)
+{
+  uint32_t lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (isfinite(v[a])) { const uint32_t k = loc_fkey(v[a]); lo[a] = min(lo[a], k); hi[a] = max(hi[a], k); }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&keys[a], lo[a]); atomicMax(&keys[3 + a], hi[a]); }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_loc_cell_count(const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z, uint64_t n, const LocGrid g,
+                 uint32_t * __restrict__ count)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    atomicAdd(&count[loc_cell(g, x[i], y[i], z[i])], 1u);
+  }
+}
+
+// one CTA: start[c] = exclusive prefix of count over the cells, start[n_cells] = total; count is cleared for the fill pass
+__global__ void __launch_bounds__(1024)
+k_loc_cell_scan(uint32_t * __restrict__ count, uint32_t * __restrict__ start, uint32_t n_cells)
+{
+  __shared__ uint32_t s_sum[1024];
+  const uint32_t tid = threadIdx.x, per = (n_cells + 1023u) / 1024u;
+  const uint32_t b0 = min(tid * per, n_cells), b1 = min(b0 + per, n_cells);
+  uint32_t sum = 0;
+  for (uint32_t i = b0; i < b1; i++) { sum += count[i]; }
+  s_sum[tid] = sum;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {
+    const uint32_t v = tid >= off ? s_sum[tid - off] : 0u;
+    __syncthreads();
+    s_sum[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = s_sum[tid] - sum;
+  for (uint32_t i = b0; i < b1; i++) { const uint32_t v = count[i]; start[i] = run; run += v; count[i] = 0; }
+  if (tid == 1023) { start[n_cells] = s_sum[1023]; }
+}
+
+__global__ void __launch_bounds__(256)
+k_loc_cell_fill(const double * __restrict__ x, const double * __restrict__ y, const double * __restrict__ z, uint64_t n, const LocGrid g,
+                uint32_t * __restrict__ fill, double * __restrict__ gx, double * __restrict__ gy, double * __restrict__ gz, uint32_t * __restrict__ gidx)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double px = x[i], py = y[i], pz = z[i];
+    const uint32_t c = loc_cell(g, px, py, pz);
+    const uint32_t at = g.cell_start[c] + atomicAdd(&fill[c], 1u);
+    gx[at] = px; gy[at] = py; gz[at] = pz; gidx[at] = (uint32_t)i;
+  }
+}
+
+template<int K>
+__global__ void __launch_bounds__(LOC_KNN_WARPS * 32)
+k_loc_knn_grid(const LocGrid g, const float4 * __restrict__ scan, uint32_t n_q, const LocPose T, uint32_t * __restrict__ out_idx,
+               double * __restrict__ out_d2)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t q = blockIdx.x * LOC_KNN_WARPS + warp;
+  if (q >= n_q) { return; }
+  double qx, qy, qz;
+  {
+    const float4 p = scan[q];
+    loc_transform(T, (double)p.x, (double)p.y, (double)p.z, qx, qy, qz);
+  }
+  const int cx = loc_cell1(qx, g.x0, g.inv_c, g.nx), cy = loc_cell1(qy, g.y0, g.inv_c, g.ny), cz = loc_cell1(qz, g.z0, g.inv_c, g.nz);
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  double bd[K];
+  uint32_t bi[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) { bd[j] = inf; bi[j] = 0xFFFFFFFFu; }
+  // all points of the cells [xa, xb] of row (y, z): one contiguous range
+  auto visit = [&](int xa, int xb, int y, int z) {
+    xa = max(xa, 0); xb = min(xb, g.nx - 1);
+    if (xa > xb) { return; }
+    const uint32_t row = ((uint32_t)z * (uint32_t)g.ny + (uint32_t)y) * (uint32_t)g.nx;
+    const uint32_t a = g.cell_start[row + (uint32_t)xa], b = g.cell_start[row + (uint32_t)xb + 1u];
+    for (uint32_t i = a + (uint32_t)lane; i < b; i += 32) {
+      // nanoflann L2_Adaptor::evalMetric for three dimensions: result += diff * diff, dimension by dimension
+      const double dx = __dsub_rn(qx, g.gx[i]), dy = __dsub_rn(qy, g.gy[i]), dz = __dsub_rn(qz, g.gz[i]);
+      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      const uint32_t id = g.gidx[i];
+      if (loc_before(d2, id, bd[K - 1], bi[K - 1])) {
+        bd[K - 1] = d2; bi[K - 1] = id;
+#pragma unroll
+        for (int j = K - 1; j > 0; j--) {
+          if (loc_before(bd[j], bi[j], bd[j - 1], bi[j - 1])) {
+            const double td = bd[j]; bd[j] = bd[j - 1]; bd[j - 1] = td;
+            const uint32_t ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
+          }
+        }
+      }
+    }
+  };
+  for (int s = 0;; s++) {
+    for (int dz = -s; dz <= s; dz++) {
+      const int z = cz + dz;
+      if (z < 0 || z >= g.nz) { continue; }
+      for (int dy = -s; dy <= s; dy++) {
+        const int y = cy + dy;
+        if (y < 0 || y >= g.ny) { continue; }
+        if (s == 0 || dz == -s || dz == s || dy == -s || dy == s) { visit(cx - s, cx + s, y, z); }   // a face of the shell
+        else { visit(cx - s, cx - s, y, z); visit(cx + s, cx + s, y, z); }                           // its two end cells
+      }
+    }
+    // nothing outside the cube [c - s, c + s]^3 is closer than the nearest of its faces that has cells behind it
+    double bound = inf;
+    if (cx - s > 0) { bound = fmin(bound, qx - (g.x0 + (double)(cx - s) * g.c)); }
+    if (cx + s < g.nx - 1) { bound = fmin(bound, (g.x0 + (double)(cx + s + 1) * g.c) - qx); }
+    if (cy - s > 0) { bound = fmin(bound, qy - (g.y0 + (double)(cy - s) * g.c)); }
+    if (cy + s < g.ny - 1) { bound = fmin(bound, (g.y0 + (double)(cy + s + 1) * g.c) - qy); }
+    if (cz - s > 0) { bound = fmin(bound, qz - (g.z0 + (double)(cz - s) * g.c)); }
+    if (cz + s < g.nz - 1) { bound = fmin(bound, (g.z0 + (double)(cz + s + 1) * g.c) - qz); }
+    if (bound == inf) { break; }                       // the cube covers the whole grid
+    bound = bound - 1.0e-6 * g.c;                      // (cell assignment rounds at ~1e-16 of the coordinates)
+    int closer = 0;
+    if (bound > 0.0) {
+      const double b2 = bound * bound;
+#pragma unroll
+      for (int j = 0; j < K; j++) { closer += bd[j] < b2 ? 1 : 0; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { closer += __shfl_xor_sync(0xFFFFFFFFu, closer, o); }
+    if (closer >= K) { break; }
+  }
+  // merge: K rounds, every lane offers the head of its list
+  for (int r = 0; r < K; r++) {
+    double d = bd[0];
+    uint32_t id = bi[0];
+    int src = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xFFFFFFFFu, d, o);
+      const uint32_t oi = __shfl_xor_sync(0xFFFFFFFFu, id, o);
+      const int os = __shfl_xor_sync(0xFFFFFFFFu, src, o);
+      if (loc_before(od, oi, d, id)) { d = od; id = oi; src = os; }
+    }
+    if (lane == 0) { out_idx[(size_t)q * K + r] = id; out_d2[(size_t)q * K + r] = d; }
+    if (lane == src) {   // the winner's list moves up
+#pragma unroll
+      for (int j = 0; j < K - 1; j++) { bd[j] = bd[j + 1]; bi[j] = bi[j + 1]; }
+      bd[K - 1] = inf; bi[K - 1] = 0xFFFFFFFFu;
+    }
+  }
+}
+
 // ---- small dense pieces (one thread per feature)
 
 struct V3 { double x, y, z; };

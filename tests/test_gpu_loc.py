@@ -74,3 +74,35 @@ def test_errors():
             prob.make_edge(np.zeros((2, 3), np.float32), [0, 0, 0, 1], [0, 0, 0])   # fewer map points than neighbours
         with pytest.raises(ExtractionError):
             LoamProblem(fe, np.zeros((40, 3), np.float32), None, n_neighbors=17).make_edge(np.zeros((2, 3), np.float32), [0, 0, 0, 1], [0, 0, 0])
+
+
+@pytest.mark.parametrize("cell", ["", "0.25", "7.0"])
+def test_grid_search_returns_the_exhaustive_neighbour_lists(cell, monkeypatch):
+    """k_loc_knn_grid (uniform grid, shell-by-shell with an exact stopping rule) against the exhaustive k_loc_knn on a
+    map with dense clusters, thin structures, duplicates, far outliers, and queries inside, at the rim and far outside
+    the map's bounding box; also with cells much smaller / larger than the default (LFX_LOC_CELL)."""
+    from lidar_feature_extraction_b200 import FeatureExtraction, LoamProblem
+
+    rng = np.random.default_rng(11)
+    wall = np.stack([rng.uniform(-40, 40, 20000), np.full(20000, 12.5), rng.uniform(-2, 6, 20000)], axis=1)
+    blobs = np.concatenate([rng.normal(c, 0.7, size=(3000, 3)) for c in ([0, 0, 0], [25, -8, 1], [-30, 3, 2])])
+    ground = np.stack([rng.uniform(-60, 60, 30000), rng.uniform(-60, 60, 30000), rng.normal(-1.8, 0.02, 30000)], axis=1)
+    far = rng.uniform(-900, 900, size=(40, 3))
+    m = np.concatenate([wall, blobs, ground, far, blobs[:500]]).astype(np.float32)
+    scan = np.concatenate([rng.uniform(-50, 50, size=(3000, 3)), rng.normal([25, -8, 1], 0.5, size=(500, 3)),
+                           rng.uniform(-3000, 3000, size=(200, 3)), m[::997].astype(np.float64)]).astype(np.float32)
+    q = np.array([0.02, -0.01, 0.3, 1.0])
+    q /= np.linalg.norm(q)
+    t = np.array([1.5, -2.0, 0.3])
+    lists = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LFX_LOC_EXHAUSTIVE", mode)
+        if cell:
+            monkeypatch.setenv("LFX_LOC_CELL", cell)
+        with FeatureExtraction() as fe:
+            prob = LoamProblem(fe, m, m[:4000], n_neighbors=15)
+            Je, re, nbe = prob.make_edge(scan, q, t, want_neighbors=True)
+            Js, rs, nbs = prob.make_surface(scan[:500], q, t, want_neighbors=True)
+        lists[mode] = (Je, re, nbe, Js, rs, nbs)
+    for a, b in zip(lists["1"], lists["0"]):
+        assert np.array_equal(a, b)

@@ -38,7 +38,8 @@ def main():
     q, t = np.array([0.0, 0.0, 0.0, 1.0]), np.zeros(3)
     out = {"metric": "features_per_sec_residual_build", "unit": "features/s",
            "config": {"edge_map": args.edge_map, "surface_map": args.surface_map, "edge_features": args.edge,
-                      "surface_features": args.surface, "n_neighbors": 15, "search": "exhaustive, exact"}}
+                      "surface_features": args.surface, "n_neighbors": 15,
+                      "search": "exhaustive, exact" if os.environ.get("LFX_LOC_EXHAUSTIVE", "0") not in ("", "0") else "uniform grid (1 m cells), exact"}}
     with FeatureExtraction() as fe:
         prob = LoamProblem(fe, torch.from_numpy(em).cuda(), torch.from_numpy(sm).cuda(), 15)
         d_es, d_ss = torch.from_numpy(es).cuda(), torch.from_numpy(ss).cuda()
