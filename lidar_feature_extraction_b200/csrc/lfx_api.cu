@@ -332,7 +332,7 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   pa.P = h->params.padding;
   pa.B = h->params.n_blocks;
   pa.enabled = h->fast_enabled ? 1 : 0;
-  k_probe_layout<<<n_scans, PROBE_THREADS, sizeof(uint32_t) * (3 * max_rings + 1), h->stream>>>(pa);
+  k_probe_layout<<<n_scans, PROBE_LAYOUT_THREADS, sizeof(uint32_t) * (3 * max_rings + 1), h->stream>>>(pa);
   if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[1], h->stream, ev_flags)); }
   if (h->fast_enabled) {
     for (int c = 0; c < N_FAST_K; c++) {

@@ -62,15 +62,20 @@ def main():
     if os.path.exists(ref):
         L = C.CDLL(ref)
         L.ref_knn.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
-        secs = 0.0
+        secs, build = 0.0, 0.0
         for m, s in ((em, es), (sm, ss)):
             md, qd = np.ascontiguousarray(m[:, :3], np.float64), np.ascontiguousarray(s[:, :3], np.float64)
             idx, d2 = np.zeros((len(qd), 15), np.uint64), np.zeros((len(qd), 15))
             t0 = time.perf_counter()
             L.ref_knn(md.ctypes.data, len(md), 3, 10, qd.ctypes.data, len(qd), 15, idx.ctypes.data, d2.ctypes.data)
             secs += time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": (args.edge + args.surface) / secs, "unit": "features/s", "cores": 1, "kind": "reference",
-                               "sample": "nanoflann kd-tree build + 15-NN of the same queries (neighbour search only, no residuals)"}
+            t0 = time.perf_counter()
+            L.ref_knn(md.ctypes.data, len(md), 3, 10, qd.ctypes.data, 0, 15, idx.ctypes.data, d2.ctypes.data)   # the build alone
+            build += time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": (args.edge + args.surface) / max(secs - build, 1e-9), "unit": "features/s", "cores": 1, "kind": "reference",
+                               "sample": f"nanoflann 15-NN of the same queries, queries only (the kd-tree build, {build:.3f} s per map pair, is "
+                                         "excluded: the reference builds it once per map, not per iteration); neighbour search only, no residuals",
+                               "with_build": (args.edge + args.surface) / secs}
     print(json.dumps(out))
 
 
