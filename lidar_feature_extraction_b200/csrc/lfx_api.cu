@@ -82,6 +82,8 @@ struct lfx_handle
   int device = 0;
   int num_sms = 0;
   int ring_grid = 0, pack_grid = 0, big_grid = 0;
+  cudaStream_t aux_stream = nullptr;   // only ever captures the body of the batch graph's conditional node
+  bool cond_ok = false;                // conditional graph nodes are used (LFX_NO_COND=1 turns them off)
   bool ring_enabled = true;   // the on-chip per-ring kernel covers these parameters (else every ring takes k_extract_rings_big)
   int tile = TILE_SMALL;   // points per ingest tile (TILE_BIG when the scatter's shared memory fits)
   size_t ring_smem = 0;
@@ -358,8 +360,40 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   }
   if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[2], h->stream, ev_flags)); }
   // ---- general path for the scans flagged by the probe or by a failed check of the sector kernel
+  // Inside a captured graph (without stage events) everything between here and the packing is the body of an IF node
+  // whose condition k_general_list sets: a batch of regular scans skips the nine launches of the general path.
+  cudaGraphConditionalHandle cond_handle = 0;
+  cudaGraph_t cap_graph = nullptr;
+  const bool use_cond = capturing && !with_events && h->cond_ok;
+  if (use_cond) {
+    cudaStreamCaptureStatus cs;
+    LFX_CUDA(h, cudaStreamGetCaptureInfo(h->stream, &cs, nullptr, &cap_graph, nullptr, nullptr));
+    LFX_CUDA(h, cudaGraphConditionalHandleCreate(&cond_handle, cap_graph, 0, cudaGraphCondAssignDefault));
+  }
   k_general_list<<<1, 1024, 0, h->stream>>>(h->d_scans.p, n_scans, h->d_scan_flags.p, h->d_gen_scan.p, h->d_gen_tile_base.p,
-                                            h->d_tile_owner.p, h->d_counters);
+                                            h->d_tile_owner.p, h->d_counters, cond_handle, use_cond ? 1 : 0);
+  struct StreamRestore   // an error return below must not leave the handle on the capture stream of the body
+  {
+    lfx_handle * h; cudaStream_t s;
+    ~StreamRestore() { h->stream = s; }
+  } restore{h, h->stream};
+  cudaStream_t outer_stream = h->stream;
+  if (use_cond) {
+    cudaStreamCaptureStatus cs;
+    const cudaGraphNode_t * deps = nullptr;
+    size_t n_deps = 0;
+    LFX_CUDA(h, cudaStreamGetCaptureInfo(h->stream, &cs, nullptr, &cap_graph, &deps, &n_deps));
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = cond_handle;
+    np.conditional.type = cudaGraphCondTypeIf;
+    np.conditional.size = 1;
+    cudaGraphNode_t cond_node = nullptr;
+    LFX_CUDA(h, cudaGraphAddNode(&cond_node, cap_graph, deps, n_deps, &np));
+    LFX_CUDA(h, cudaStreamUpdateCaptureDependencies(h->stream, &cond_node, 1, cudaStreamSetCaptureDependencies));
+    LFX_CUDA(h, cudaStreamBeginCaptureToGraph(h->aux_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    h->stream = h->aux_stream;   // the launches below go into the body
+  }
   const int ingest_grid = (int)std::min<uint32_t>(std::max<uint32_t>(n_tiles, 1u), (uint32_t)h->ingest_grid);
   if (h->tile == TILE_BIG) {
     k_ring_hist<TILE_BIG><<<ingest_grid, INGEST_THREADS, sizeof(uint32_t) * max_rings, h->stream>>>(
@@ -452,6 +486,11 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
     ba.prm = h->dev;
     k_extract_rings_big<<<h->big_grid, BIG_THREADS, 0, h->stream>>>(ba);
   }
+  if (use_cond) {
+    h->stream = outer_stream;
+    cudaGraph_t body = nullptr;
+    LFX_CUDA(h, cudaStreamEndCapture(h->aux_stream, &body));
+  }
   if (with_events) { LFX_CUDA(h, cudaEventRecordWithFlags(h->ev[5], h->stream, ev_flags)); }
   // ---- packing
   k_feat_offsets_a<<<n_scans, 128, 0, h->stream>>>(h->d_rings.p, h->d_ring_featoff.p, h->d_counts.p, max_rings);
@@ -479,7 +518,14 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   return LFX_OK;
 }
 
-int kernels_per_batch(const lfx_handle * h) { return (h->fast_enabled ? 11 + 2 * N_FAST_K + 1 : 11) + (h->ring_enabled ? 1 : 0); }
+// kernels of one batch; `conditional`: the batch ran as a graph whose general path is the body of an IF node - its
+// kernels (ingest x3, ring probe, indexed sector kernels, per-ring kernels) are then not counted: a lower bound
+int kernels_per_batch(const lfx_handle * h, bool conditional)
+{
+  const int all = (h->fast_enabled ? 11 + 2 * N_FAST_K + 1 : 11) + (h->ring_enabled ? 1 : 0);
+  const int body = 4 + (h->fast_enabled ? N_FAST_K : 0) + (h->ring_enabled ? 1 : 0) + 1;
+  return conditional ? all - body : all;
+}
 
 }  // namespace
 
@@ -562,6 +608,12 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   else {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { return bail(e, "cudaStreamCreate"); }
     h->own_stream = true;
+  }
+
+  if ((e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) { return bail(e, "cudaStreamCreate(aux)"); }
+  {
+    const char * nc = getenv("LFX_NO_COND");
+    h->cond_ok = !(nc && atoi(nc) != 0);
   }
 
   // derived constants
@@ -670,6 +722,7 @@ void lfx_destroy(lfx_handle * h)
   for (auto & ev : h->desc_done) { if (ev) { cudaEventDestroy(ev); } }
   cudaFreeHost(h->h_edge); cudaFreeHost(h->h_surface); cudaFreeHost(h->h_labels); cudaFreeHost(h->h_sorted_src);
   for (auto & ev : h->ev) { if (ev) { cudaEventDestroy(ev); } }
+  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); }
   if (h->own_stream && h->stream) { cudaStreamDestroy(h->stream); }
   delete h;
 }
@@ -872,7 +925,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
       if ((rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, h->timing))) { return rc; }
       h->have_timing = h->timing;
     }
-    h->launches += kernels_per_batch(h);
+    h->launches += kernels_per_batch(h, use_graph && !timed_graph && h->cond_ok);
   } else {
     LFX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * C_COUNT, h->stream));
     LFX_CUDA(h, cudaMemsetAsync(h->d_offsets.p, 0, sizeof(uint32_t) * 2, h->stream));

@@ -157,7 +157,7 @@ __device__ __forceinline__ int find_gen_scan(const uint32_t * gen_tile_base, int
 static __global__ void __launch_bounds__(1024)
 k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t * __restrict__ scan_flags,
                uint32_t * __restrict__ gen_scan, uint32_t * __restrict__ gen_tile_base, uint32_t * __restrict__ tile_owner,
-               uint32_t * counters)
+               uint32_t * counters, cudaGraphConditionalHandle cond, int use_cond)
 {
   __shared__ uint32_t s_c[1024], s_t[1024];
   const int tid = threadIdx.x;
@@ -183,7 +183,11 @@ k_general_list(const ScanDesc * __restrict__ scans, int n_scans, const uint32_t 
     carry_c += s_c[1023]; carry_t += s_t[1023];
     __syncthreads();
   }
-  if (tid == 0) { gen_tile_base[carry_c] = carry_t; counters[C_GEN_SCANS] = carry_c; counters[C_GEN_TILES] = carry_t; }
+  if (tid == 0) {
+    gen_tile_base[carry_c] = carry_t; counters[C_GEN_SCANS] = carry_c; counters[C_GEN_TILES] = carry_t;
+    // inside a CUDA graph the whole general path is the body of an IF node: it only runs when a scan needs it
+    if (use_cond) { cudaGraphSetConditional(cond, carry_c != 0 ? 1u : 0u); }
+  }
   __syncthreads();
   // general tile -> its entry of gen_scan: one warp per flagged scan, lanes on consecutive tiles (coalesced)
   for (uint32_t k = (uint32_t)tid >> 5; k < carry_c; k += 32) {
