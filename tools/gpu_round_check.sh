@@ -11,6 +11,8 @@ timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json
 timeout 300 python tools/bench_convert.py --scans 1250 > gpurun_out/${tag}_bench_convert.json 2>> gpurun_out/${tag}_bench.err
 timeout 300 python tools/bench_loc.py > gpurun_out/${tag}_bench_loc.json 2>> gpurun_out/${tag}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_os128x1250.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-workloads > /dev/null 2>&1
+# the same with the conditional node off (LFX_NO_COND=1): every kernel of the general path is launched and listed
+LFX_NO_COND=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_os128x1250_nocond.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-workloads > /dev/null 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_hdl64x256.csv python bench.py --workload hdl64x256 --steps 2 --warmup 3 --no-e2e --no-cpu --no-workloads > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_extract_sectors -s 7 -c 1 -o gpurun_out/${tag}_sector -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-workloads > /dev/null 2>&1
 # the small kernels of the regular path and the ragged path's kernels: one full-set pass each, summaries only
