@@ -342,7 +342,8 @@ def stage_times(fe, views, keep, mode: int, sync: bool, iters: int):
     return np.array(rows[1:])
 
 
-def measure_workload(name: str, local_rank: int, dev, stream, steps: int, peak: float, rank: int = 0, world: int = 1) -> dict:
+def measure_workload(name: str, local_rank: int, dev, stream, steps: int, peak: float, rank: int = 0, world: int = 1,
+                     parity_scans: int = -1) -> dict:
     """One of the other BASELINE.json configs, device-resident: same timing rules as the headline (CUDA events on the
     launching stream, >= 3 warm-up steps, inputs larger than L2), fewer extras. world > 1: every rank extracts its own
     shard of world x scans frames and the per-scan counts are exchanged each step (lfx_shard_*); time = max over ranks,
@@ -408,6 +409,17 @@ def measure_workload(name: str, local_rank: int, dev, stream, steps: int, peak: 
            "pipeline_frac": alg_all / (ms * 1e-3) / 1e9 / (peak * world), "kernel_frac": alg / (kernel_ms * 1e-3) / 1e9 / peak,
            "stage_ms": {k: float(stage[:, i].mean()) for i, k in enumerate(STAGES)}, "paths": fe.batch_stats(),
            "selected_fraction": n_feat / max(n_points, 1)}
+    # parity of THIS batch against the reference itself on its first scans (rank 0; CPU work bounded to ~4 M points)
+    if rank == 0 and parity_scans != 0:
+        n_par = max(2, min(scans, int(4.0e6 // max(n_points // scans, 1)))) if parity_scans < 0 else min(parity_scans, scans)
+        sample = d_in[: int(offs[n_par])].cpu().numpy()
+        clouds = [sample[int(offs[s]): int(offs[s + 1])] for s in range(n_par)]
+        _, kind, results = cpu_reference_pass(clouds, host_cores())
+        if results is not None:
+            fe.extract_views(views, keep=d_in)
+            out["parity"] = parity_check(fe.fetch(fetch_points=True), clouds, results, kind)
+            out["parity"].pop("label_histogram", None)
+        del sample, clouds
     if shard is not None:
         torch.cuda.synchronize()
         dist.barrier()              # no peer may still be pushing into this rank's buffers when they are released
