@@ -315,11 +315,13 @@ k_ring_plan(const ScanDesc * __restrict__ scans, const uint32_t * __restrict__ s
 
 // ------------------------------------------------------------------ ingest: stable scatter (one CTA per tile)
 
-// shared memory: [8 warps][R] positions | [R] tile count | [R] tile offset | [R] bucket base | [TILE] sorted source
-// indices | [TILE] their rings (u16) | [8 warps][R] lane probes (bytes)
+// shared memory: [8 warps][R] positions | [R] tile count | [R] tile offset | [R] bucket base | [TILE + R] sorted source
+// indices | [TILE + R] their rings (u16) | [8 warps][R] lane probes (bytes). The runs of consecutive rings are one word
+// apart more than their lengths: a spinning sensor gives every ring (nearly) the same number of points per tile, a
+// multiple of 32 for whole columns, and without the skew 32 lanes with 32 consecutive ring ids would write into ONE bank.
 __host__ __device__ inline size_t scatter_smem_bytes(int max_rings, int tile)
 {
-  return (size_t)(INGEST_THREADS / 32) * max_rings * 5 + (size_t)max_rings * 12 + (size_t)tile * 6;
+  return (size_t)(INGEST_THREADS / 32) * max_rings * 5 + (size_t)max_rings * 12 + (size_t)(tile + max_rings) * 6 + 8;
 }
 
 template<int TILE>
@@ -343,8 +345,8 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
   uint32_t * toff = tcount + R;
   uint32_t * gbase = toff + R;
   uint32_t * s_out = gbase + R;
-  uint16_t * s_ring = reinterpret_cast<uint16_t *>(s_out + TILE);
-  uint8_t * probe = reinterpret_cast<uint8_t *>(s_ring + TILE) + warp * R;
+  uint16_t * s_ring = reinterpret_cast<uint16_t *>(s_out + TILE + R);
+  uint8_t * probe = reinterpret_cast<uint8_t *>(s_ring + ((TILE + R + 3) & ~3)) + warp * R;
   __shared__ uint32_t s_total;
   // software pipeline over the CTA's tiles: the descriptor chain (three dependent loads) is fetched two tiles ahead,
   // the ring ids and (for up to 256 rings) the bucket bases one tile ahead, so that none of these latencies is paid
@@ -402,10 +404,15 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
         uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) { inc += u; } }
-        if (r0 + lane < R) { toff[r0 + lane] = carry + inc - v; }
+        // (+ one pad word per ring, marked below: the skew that keeps the runs of consecutive rings in different banks)
+        if (r0 + lane < R) {
+          const uint32_t at = carry + inc - v + (uint32_t)(r0 + lane);
+          toff[r0 + lane] = at;
+          s_ring[at + v] = 0xFFFFu;
+        }
         carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
       }
-      if (lane == 0) { s_total = carry; }
+      if (lane == 0) { s_total = carry + (uint32_t)R; }
     }
     __syncthreads();
 #pragma unroll
@@ -443,7 +450,7 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
     // words of a ring's bucket (whole 32-byte sectors instead of 2048 scattered 4-byte stores)
     for (uint32_t e = threadIdx.x; e < s_total; e += blockDim.x) {
       const uint32_t r = s_ring[e];
-      idx[cur.point_base + gbase[r] + (e - toff[r])] = s_out[e];
+      if (r != 0xFFFFu) { idx[cur.point_base + gbase[r] + (e - toff[r])] = s_out[e]; }
     }
     cur = nxt; nxt = nxt2; base0 = base0_n;
 #pragma unroll
