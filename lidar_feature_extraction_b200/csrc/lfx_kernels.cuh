@@ -448,9 +448,19 @@ k_ring_scatter(const ScanDesc * __restrict__ scans, const uint32_t * __restrict_
     __syncthreads();
     // the tile's points, now grouped by ring in stable order, go out run by run: consecutive threads write consecutive
     // words of a ring's bucket (whole 32-byte sectors instead of 2048 scattered 4-byte stores)
-    for (uint32_t e = threadIdx.x; e < s_total; e += blockDim.x) {
-      const uint32_t r = s_ring[e];
-      if (r != 0xFFFFu) { idx[cur.point_base + gbase[r] + (e - toff[r])] = s_out[e]; }
+    if (R <= 256) {
+      // a warp per ring: the run's place is looked up once, the lanes copy consecutive words
+      for (int r = warp; r < R; r += WARPS) {
+        const uint32_t n = tcount[r];
+        const uint32_t * src = s_out + toff[r];
+        uint32_t * dst = idx + cur.point_base + gbase[r];
+        for (uint32_t k = lane; k < n; k += 32) { dst[k] = src[k]; }
+      }
+    } else {
+      for (uint32_t e = threadIdx.x; e < s_total; e += blockDim.x) {
+        const uint32_t r = s_ring[e];
+        if (r != 0xFFFFu) { idx[cur.point_base + gbase[r] + (e - toff[r])] = s_out[e]; }
+      }
     }
     cur = nxt; nxt = nxt2; base0 = base0_n;
 #pragma unroll
