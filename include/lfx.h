@@ -89,7 +89,8 @@ void lfx_launch_yaml_params(lfx_params *out);
 /* Sizing and diagnostics knobs that have no counterpart in the reference. Zero = default. */
 typedef struct lfx_options {
   int device;            /* CUDA device ordinal */
-  int max_ring_points;   /* longest ring held on chip; default 2304, at most 8192 (larger values are clamped). Longer
+  int max_ring_points;   /* longest ring held on chip; default 4096, at most 8192 (larger values are clamped, and
+                          * lowered to what the device's shared memory holds). Longer
                           * rings are not refused: they run on the unbounded per-ring kernel (lfx_big.cuh) */
   int max_rings;         /* ring ids must be < max_rings; default 128, max 4096 */
   int want_sorted_src;   /* also produce the ring-sorted -> source index map (4 B/point) */

@@ -573,7 +573,9 @@ int lfx_create(const lfx_params * params, const lfx_options * options, lfx_handl
   lfx_handle * h = new lfx_handle();
   h->params = *params;
   if (options) { h->opt = *options; }
-  if (h->opt.max_ring_points <= 0) { h->opt.max_ring_points = 2304; }
+  // default: a 4096-column sweep / an HDL-64 at 5 Hz still fits the on-chip per-ring kernel (174 KB of shared memory at
+  // padding 5); regular and rotated-monotone rings of up to 372-point sectors never get there (sector kernel)
+  if (h->opt.max_ring_points <= 0) { h->opt.max_ring_points = 4096; }
   if (h->opt.max_rings <= 0) { h->opt.max_rings = 128; }
   if (h->opt.max_rings > 4096 || h->opt.force_order_path < 0 || h->opt.force_order_path > 2) {
     g_create_error = "lfx_options outside the supported envelope (max_rings <= 4096)";

@@ -98,3 +98,13 @@ def test_every_padding_up_to_eight_runs_on_the_sector_kernel(oracle, padding, se
     assert sum(stats["fast_rings"]) + sum(stats["indexed_rings"]) == 2 * synth.spec(sensor).n_rings, stats
     if sensor != "hdl64":
         assert stats["general_scans"] == 0, stats
+
+
+def test_a_4096_column_sweep_runs_on_chip_by_default(oracle):
+    """HDL-64 at 5 Hz / a 4096-column sweep: rings of ~4000 points have sectors too long for the sector kernel (683
+    positions at six sectors) but fit the on-chip per-ring kernel of a default handle (max_ring_points 4096); rings beyond
+    that take the unbounded kernel. Either way the result is the oracle's."""
+    clouds = [adv.ragged_scan(5, [4096, 4000, 3600, 4097, 64], shuffle="interleave")]
+    _check(oracle, _hp(), clouds)
+    _, stats = _check(oracle, _hp(n_blocks=12), clouds)      # twelve sectors: 341 positions each, the sector kernel's size
+    assert sum(stats["indexed_rings"]) == 4, stats           # (the 64-point ring has sectors of 4 points: fine as well)
