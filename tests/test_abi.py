@@ -211,3 +211,109 @@ int main(int argc, char ** argv) {
         assert np.array_equal(got, want)
     assert np.array_equal(np.fromfile(outs[2], np.uint8), ref.labels)
     assert np.array_equal(np.fromfile(outs[3], np.uint8).reshape(-1, 32), co.colored_scan(x, y, z, ref))
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_classes_run_on_the_gpu(tmp_path):
+    """Every class of include/lfx.hpp on the device, from a C++ program: lfx::Pipeline (two handles in turn),
+    lfx::PointTypeConverter -> ExtractBatch (the deployed chain), lfx::MapBuilder, lfx::LoamProblem and a one-rank
+    lfx::Shard. The program prints what it got; the same calls through the Python mirrors must give the same numbers."""
+    import shutil
+    import subprocess
+
+    from lidar_feature_extraction_b200 import (FeatureExtraction, LoamProblem, MapBuilder, default_params, make_pose, synth)
+
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    clouds = [synth.scan_host(synth.spec("vlp16"), f) for f in (3, 4)]
+    for k, c in enumerate(clouds):
+        (tmp_path / f"scan{k}.bin").write_bytes(c.tobytes())
+    src = tmp_path / "host.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <fstream>
+#include <iterator>
+#include "lfx.hpp"
+static std::vector<char> slurp(const char * p) { std::ifstream in(p, std::ios::binary); return std::vector<char>((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()); }
+int main(int, char ** argv) {
+  try {
+    const std::vector<char> a = slurp(argv[1]), b = slurp(argv[2]);
+    const std::vector<lfx::PointField> f = {{"x", 0, 7}, {"y", 4, 7}, {"z", 8, 7}, {"intensity", 16, 7}, {"ring", 20, LFX_RING_U16}};
+    const lfx_cloud_view va = lfx::MakeView(a.data(), (uint32_t)(a.size() / 32), 32, f, true), vb = lfx::MakeView(b.data(), (uint32_t)(b.size() / 32), 32, f, true);
+    // ---- Pipeline: {a}, {a, b}, {b} through two handles, collected oldest first
+    lfx::Pipeline pipe;
+    std::vector<float> edge(4 * (a.size() + b.size()) / 32), surf(edge.size());
+    pipe.Submit({va}); pipe.Submit({va, vb});
+    const lfx::Pipeline::Output o1 = pipe.Collect(edge.data(), edge.size() / 4, surf.data(), surf.size() / 4);
+    pipe.Submit({vb});
+    const lfx::Pipeline::Output o2 = pipe.Collect(edge.data(), edge.size() / 4, surf.data(), surf.size() / 4);
+    const lfx::Pipeline::Output o3 = pipe.Collect(edge.data(), edge.size() / 4, surf.data(), surf.size() / 4);
+    std::printf("pipeline %u %u | %u %u %u %u | %u %u\n", o1.counts[0], o1.counts[1], o2.counts[0], o2.counts[1], o2.counts[2], o2.counts[3], o3.counts[0], o3.counts[1]);
+    // ---- converter -> extraction on the device (the wire layout is a raw layout like any other), then the map
+    lfx::FeatureExtraction fe;
+    lfx::PointTypeConverter conv(fe);
+    const lfx_point_field pf[5] = {{"x", 0, 7, 1}, {"y", 4, 7, 1}, {"z", 8, 7, 1}, {"intensity", 16, 7, 1}, {"ring", 20, 4, 1}};
+    std::vector<lfx_raw_cloud> raw(2);
+    raw[0] = {a.data(), a.size(), 32, pf, 5, 0, LFX_MEM_HOST};
+    raw[1] = {b.data(), b.size(), 32, pf, 5, 0, LFX_MEM_HOST};
+    const lfx_convert_result cr = conv.Convert(raw);
+    fe.ExtractBatch(conv.Views(cr.n_clouds));
+    std::vector<uint32_t> counts(4), offsets(6);
+    if (lfx_fetch_counts(fe.handle(), counts.data(), offsets.data()) != LFX_OK) { return 20; }
+    std::printf("chain %u %u | %u %u %u %u\n", cr.kept[0], cr.kept[1], counts[0], counts[1], counts[2], counts[3]);
+    // ---- one-rank shard over the same batch
+    lfx::Shard shard(fe, {}, 0, 1, 2);
+    shard.Exchange();
+    std::vector<uint32_t> gc; std::vector<uint64_t> go;
+    shard.Fetch(gc, go, 2);
+    std::printf("shard %u %u %u %u | %llu %llu\n", gc[0], gc[1], gc[2], gc[3], (unsigned long long)go[4], (unsigned long long)go[5]);
+    lfx::MapBuilder map(fe);
+    const lfx_pose p0{{0, 0, 0}, {0, 0, 0, 1}}, p1{{2.5, 0, 0}, {0, 0, 0.0998334166, 0.9950041653}};
+    const std::vector<uint8_t> sel = map.AddBatch({p0, p1});
+    const std::vector<float> pts = map.Points();
+    double sum = 0;
+    for (float v : pts) { sum += v; }
+    std::printf("map %d %d %llu %.9e\n", (int)sel[0], (int)sel[1], (unsigned long long)map.Size(), sum);
+    // ---- residual rows of scan b's edges against the map built from both frames
+    if (lfx_fetch_features(fe.handle(), edge.data(), edge.size() / 4, surf.data(), surf.size() / 4) != LFX_OK) { return 21; }
+    lfx::LoamProblem prob(fe, pts.data(), pts.size() / 4, surf.data(), offsets[5], 15);
+    std::vector<double> J, r;
+    prob.Edge(edge.data() + 4 * offsets[2], counts[2], p1, J, r);
+    double sj = 0, sr = 0;
+    for (double v : J) { sj += v < 0 ? -v : v; }
+    for (double v : r) { sr += v < 0 ? -v : v; }
+    std::printf("loam %zu %.9e %.9e\n", r.size(), sj, sr);
+    return 0;
+  } catch (const lfx::Error & e) {
+    std::printf("error %d: %s\n", e.code, e.what());
+    return 14;
+  }
+}
+''')
+    exe = tmp_path / "host"
+    pkg = os.path.join(root, "lidar_feature_extraction_b200")
+    subprocess.run([cxx, "-std=c++17", "-Wall", "-Werror", f"-I{root}/include", str(src), "-o", str(exe),
+                    f"-L{pkg}", "-llfx", f"-Wl,-rpath,{pkg}"], check=True)
+    r = subprocess.run([str(exe), str(tmp_path / "scan0.bin"), str(tmp_path / "scan1.bin")], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    got = {line.split()[0]: line.split()[1:] for line in r.stdout.strip().splitlines()}
+
+    q1 = [0.0, 0.0, 0.0998334166, 0.9950041653]
+    with FeatureExtraction(default_params(), device=0) as fe:
+        out = fe.extract_batch(clouds, fetch_points=False)
+        ca, cb = [int(v) for v in out.counts[0]], [int(v) for v in out.counts[1]]
+        mb = MapBuilder(fe)
+        sel = mb.add_batch([make_pose([0, 0, 0], [0, 0, 0, 1]), make_pose([2.5, 0, 0], q1)])
+        pts = mb.points()
+        prob = LoamProblem(fe, pts, out.surface_xyz, n_neighbors=15)
+        J, res = prob.make_edge(out.scan_edges(1), q1, [2.5, 0, 0])
+    assert [int(v) for v in got["pipeline"] if v != "|"] == ca + ca + cb + cb
+    assert [int(v) for v in got["chain"] if v != "|"] == [len(clouds[0]), len(clouds[1])] + ca + cb   # no (0,0,0) points: all kept
+    assert [int(v) for v in got["shard"] if v != "|"] == ca + cb + [ca[0] + cb[0], ca[1] + cb[1]]
+    assert [int(got["map"][0]), int(got["map"][1]), int(got["map"][2])] == [int(sel[0]), int(sel[1]), len(pts)]
+    assert abs(float(got["map"][3]) - float(np.asarray(pts, np.float64).sum())) <= 1e-3 * max(1.0, abs(float(np.asarray(pts, np.float64).sum())))
+    assert int(got["loam"][0]) == res.size
+    assert abs(float(got["loam"][1]) - np.abs(J).sum()) <= 1e-6 * np.abs(J).sum() + 1e-9
+    assert abs(float(got["loam"][2]) - np.abs(res).sum()) <= 1e-6 * np.abs(res).sum() + 1e-9
