@@ -314,6 +314,8 @@ int validate_params(const lfx_params & p, std::string & why)
   return LFX_OK;
 }
 
+constexpr int COND_MIN_SCANS = 32;   // smallest batch whose graph wraps the general path in a conditional node
+
 // ---- the batch pipeline (enqueued on h->stream; also the body of the captured graph)
 int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_events, bool capturing = false)
 {
@@ -364,7 +366,9 @@ int enqueue_pipeline(lfx_handle * h, int n_scans, uint32_t n_tiles, bool with_ev
   // whose condition k_general_list sets: a batch of regular scans skips the nine launches of the general path.
   cudaGraphConditionalHandle cond_handle = 0;
   cudaGraph_t cap_graph = nullptr;
-  const bool use_cond = capturing && !with_events && h->cond_ok;
+  // (only for batches of at least COND_MIN_SCANS scans: for a handful of scans the node costs about what it saves, and
+  //  the per-scan entry of the ROS callback stays a plain sequence of kernel nodes)
+  const bool use_cond = capturing && !with_events && h->cond_ok && n_scans >= COND_MIN_SCANS;
   if (use_cond) {
     cudaStreamCaptureStatus cs;
     LFX_CUDA(h, cudaStreamGetCaptureInfo(h->stream, &cs, nullptr, &cap_graph, nullptr, nullptr));
@@ -927,7 +931,7 @@ int lfx_extract_batch(lfx_handle * h, const lfx_cloud_view * scans, int n_scans,
       if ((rc = enqueue_pipeline(h, n_scans, (uint32_t)total_tiles, h->timing))) { return rc; }
       h->have_timing = h->timing;
     }
-    h->launches += kernels_per_batch(h, use_graph && !timed_graph && h->cond_ok);
+    h->launches += kernels_per_batch(h, use_graph && !timed_graph && h->cond_ok && n_scans >= COND_MIN_SCANS);
   } else {
     LFX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, sizeof(uint32_t) * C_COUNT, h->stream));
     LFX_CUDA(h, cudaMemsetAsync(h->d_offsets.p, 0, sizeof(uint32_t) * 2, h->stream));
