@@ -494,6 +494,27 @@ def measure_chain(local_rank: int, dev, stream, steps: int, peak: float, scans: 
     out = {"ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "raw points/s", "steps": steps, "points_per_step": n, "scans": scans,
            "kept_fraction": kept / n, "algorithmic_bytes": alg, "pipeline_frac": alg / (ms * 1e-3) / 1e9 / peak,
            "convert_kernel_ms": float(cms.value), "stage_ms": {k: float(st[i]) for i, k in enumerate(STAGES)}, "paths": fe.batch_stats()}
+    # parity of THIS chain batch: the converted bytes of the first clouds against the converter's CPU restatement
+    # (oracle/convert_oracle.py, pinned to the reference's convert.py), and the features extracted from them against
+    # the reference's extraction of those converted clouds
+    try:
+        from oracle import convert_oracle as co
+
+        n_par = max(2, min(scans, int(4.0e6 // per)))
+        host_conv, conv_bad = [], 0
+        ofields = [co.Field(f.name, f.offset, f.datatype) for f in fields]
+        for s in range(n_par):
+            got = conv.fetch(s)
+            want, _ = co.convert(raw3[s].cpu().numpy(), ofields, 48)
+            conv_bad += 0 if np.array_equal(got, want) else 1
+            host_conv.append(got)
+        _, kind, results = cpu_reference_pass(host_conv, host_cores())
+        if results is not None:
+            out["parity"] = parity_check(fe.fetch(fetch_points=True), host_conv, results, kind)
+            out["parity"].pop("label_histogram", None)
+            out["parity"]["converter"] = {"clouds": n_par, "mismatches": conv_bad, "against": "port (oracle/convert_oracle.py, pinned to convert.py's outputs)"}
+    except Exception as e:   # the checker must not take the measurement down
+        out["parity"] = {"error": repr(e)}
     conv.close()
     fe.close()
     del raw, raw3, msgs
