@@ -108,3 +108,30 @@ def test_a_4096_column_sweep_runs_on_chip_by_default(oracle):
     _check(oracle, _hp(), clouds)
     _, stats = _check(oracle, _hp(n_blocks=12), clouds)      # twelve sectors: 341 positions each, the sector kernel's size
     assert sum(stats["indexed_rings"]) == 4, stats           # (the 64-point ring has sectors of 4 points: fine as well)
+
+
+@pytest.mark.parametrize("n_ragged", [0, 1, 17, 48])
+def test_batches_big_enough_for_the_conditional_node(oracle, n_ragged):
+    """From 32 scans on, the batch graph wraps the general path in an IF node whose condition a kernel sets on the
+    device (lfx_api.cu, COND_MIN_SCANS): batches with no, one, some and only ragged scans, replayed from the cached
+    graph with the ragged scans at other places, must all come out as the oracle has them."""
+    from lidar_feature_extraction_b200 import synth
+
+    sp = synth.spec("vlp16")
+    regular = [synth.scan_host(sp, f) for f in range(6)]
+    ragged = [adv.ragged_scan(40 + k, [300, 97, 0, 640, 23, 1200][k % 6:] + [150], shuffle=["interleave", "random", "rotate"][k % 3])
+              for k in range(6)]
+    n = 48
+    order_a = [i < n_ragged for i in range(n)]
+    order_b = [i >= n - n_ragged for i in range(n)]
+    hp = _hp()
+    from oracle import binding as ob
+
+    with _fe(hp) as fe:
+        for order in (order_a, order_b, order_a):
+            clouds = [ragged[i % 6] if is_r else regular[i % 6] for i, is_r in enumerate(order)]
+            out = fe.extract_batch(clouds)
+            stats = fe.batch_stats()
+            assert stats["general_scans"] == n_ragged, stats
+            for s in (0, 1, 16, 17, 30, 31, 46, 47):
+                compare_scan(out, s, clouds[s], oracle.extract_scan(clouds[s], oracle_params(ob, hp)))
