@@ -56,6 +56,23 @@ def test_invalid_parameters_are_rejected_before_touching_cuda():
         assert b"> 0" in lib.lfx_last_error(None)
 
 
+def test_large_padding_and_sector_counts_pass_validation():
+    """The reference has no upper bound on convolution_padding / n_blocks (hyper_parameter.hpp:45-53): such handles are
+    created (k_extract_rings_big runs them); without a device the only error left is LFX_E_CUDA."""
+    import torch
+
+    lib = N.lib()
+    for padding, n_blocks in ((20, 6), (5, 100), (64, 300)):
+        p = N.Params()
+        lib.lfx_default_params(C.byref(p))
+        p.padding, p.n_blocks = padding, n_blocks
+        h = C.c_void_p()
+        rc = lib.lfx_create(C.byref(p), None, C.byref(h))
+        assert rc == (N.LFX_OK if torch.cuda.is_available() else N.LFX_E_CUDA), (rc, lib.lfx_last_error(None))
+        if rc == N.LFX_OK:
+            lib.lfx_destroy(h)
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
 
@@ -67,6 +84,11 @@ def test_no_gpu_means_loud_failure_not_fallback():
         FeatureExtraction()
     assert e.value.code == N.LFX_E_CUDA
     assert "no CPU fallback" in str(e.value)
+    from lidar_feature_extraction_b200 import PipelinedExtraction
+
+    with pytest.raises(ExtractionError) as e:      # the two-handle pipeline has no fallback either
+        PipelinedExtraction()
+    assert e.value.code == N.LFX_E_CUDA
 
 
 def test_product_never_imports_the_oracle():
