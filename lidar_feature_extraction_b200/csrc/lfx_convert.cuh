@@ -25,9 +25,14 @@
 namespace lfxk
 {
 
-constexpr int CONV_THREADS = 256;
+// tile shape, measured on os128 x 1250 raw clouds (kernel ms): 256 threads x 2 points 7.28, 128 x 4 6.90, 512 x 2 6.96,
+// 256 x 4 7.06, 64 x 8 7.01, 128 x 8 7.35, 128 x 2 7.82: four warps per 512-point tile wait least at the tile's barriers
+#ifndef LFX_CONV_THREADS
+#define LFX_CONV_THREADS 128
+#endif
+constexpr int CONV_THREADS = LFX_CONV_THREADS;
 #ifndef LFX_CONV_PPT
-#define LFX_CONV_PPT 2
+#define LFX_CONV_PPT 4
 #endif
 constexpr int CONV_PPT = LFX_CONV_PPT;              // points per thread
 constexpr int CONV_TILE = CONV_PPT * CONV_THREADS;  // points per CTA
@@ -172,7 +177,7 @@ __device__ __forceinline__ void conv_mbar_wait(uint64_t * bar, uint32_t parity)
 }
 
 // One CTA per tile (CONV_TILE = CONV_PPT * CONV_THREADS consecutive points of one cloud). Thread t owns points t,
-// t + 256, ... of the tile: a warp's ballot covers 32 consecutive points and ranks stay stable. (A persistent
+// t + CONV_THREADS, ... of the tile: a warp's ballot covers 32 consecutive points and ranks stay stable. (A persistent
 // variant with two staging buffers measured 4x slower on B200: with all resident CTAs in lock step every
 // look-back has to walk the whole window of concurrently processed tiles.)
 // FAST: every cloud of the batch has the common plan (ConvCloud::fast): fields are single 32-bit loads and the
