@@ -1912,8 +1912,8 @@ int shard_setup(lfx_shard * s, const ShardWire * local_wires)
   }
   s->slot_words = lfxk::shard_slot_words(s->world, s->width);
   if (!local_wires) {   // (single-process groups allocate before they call this)
-    LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_recv), sizeof(uint32_t) * 2 * s->slot_words));
-    LFX_SHARD_CUDA(s, cudaMemset(s->d_recv, 0, sizeof(uint32_t) * 2 * s->slot_words));
+    LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_recv), sizeof(uint32_t) * lfxk::SHARD_SLOTS * s->slot_words));
+    LFX_SHARD_CUDA(s, cudaMemset(s->d_recv, 0, sizeof(uint32_t) * lfxk::SHARD_SLOTS * s->slot_words));
   }
   LFX_SHARD_CUDA(s, cudaMalloc(reinterpret_cast<void **>(&s->d_send), sizeof(uint32_t) * 2 * std::max<uint32_t>(s->width, 1)));
   LFX_SHARD_CUDA(s, cudaMemset(s->d_send, 0, sizeof(uint32_t) * 2 * std::max<uint32_t>(s->width, 1)));
@@ -1987,7 +1987,7 @@ int shard_setup(lfx_shard * s, const ShardWire * local_wires)
 lfxk::ShardScanArgs shard_scan_args(lfx_shard * s)
 {
   lfxk::ShardScanArgs a;
-  a.slot = s->d_recv + (size_t)(s->epoch & 1u) * s->slot_words;
+  a.slot = s->d_recv + (size_t)(s->epoch % lfxk::SHARD_SLOTS) * s->slot_words;
   a.counts_all = s->d_counts_all;
   a.offsets_all = s->d_offsets_all;
   a.status = s->d_status;
@@ -2076,8 +2076,8 @@ int lfx_shard_create_local(lfx_handle ** handles, int world, uint64_t n_frames, 
     uint32_t width = 0;
     for (int k = 0; k < world; k++) { uint64_t a, b; lfx_shard_range(n_frames, k, world, &a, &b); width = std::max<uint32_t>(width, (uint32_t)(b - a)); }
     const size_t words = lfxk::shard_slot_words(world, width);
-    if (cudaSetDevice(s->h->device) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&s->d_recv), sizeof(uint32_t) * 2 * words) != cudaSuccess ||
-        cudaMemset(s->d_recv, 0, sizeof(uint32_t) * 2 * words) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    if (cudaSetDevice(s->h->device) != cudaSuccess || cudaMalloc(reinterpret_cast<void **>(&s->d_recv), sizeof(uint32_t) * lfxk::SHARD_SLOTS * words) != cudaSuccess ||
+        cudaMemset(s->d_recv, 0, sizeof(uint32_t) * lfxk::SHARD_SLOTS * words) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
       rc = fail(handles[0], LFX_E_CUDA, "receive buffer allocation failed");
       break;
     }
@@ -2112,7 +2112,7 @@ int lfx_shard_exchange(lfx_shard * s)
     s->epoch += 1;
     lfxk::ShardPushArgs pa;
     pa.counts = h->d_counts.p; pa.n_local = n_local; pa.rank = s->rank; pa.world = s->world; pa.width = s->width; pa.epoch = s->epoch;
-    for (int p = 0; p < s->world; p++) { pa.peers.slot[p] = s->peer_recv[p] + (size_t)(s->epoch & 1u) * s->slot_words; }
+    for (int p = 0; p < s->world; p++) { pa.peers.slot[p] = s->peer_recv[p] + (size_t)(s->epoch % lfxk::SHARD_SLOTS) * s->slot_words; }
     if (scan_first) { lfxk::k_shard_scan_push<<<1, lfxk::SHARD_THREADS, 0, h->stream>>>(sa, pa); s->finished = s->epoch - 1; }
     else { lfxk::k_shard_push<<<1, lfxk::SHARD_THREADS, 0, h->stream>>>(pa); }
     LFX_SHARD_CUDA(s, cudaGetLastError());
@@ -2122,7 +2122,7 @@ int lfx_shard_exchange(lfx_shard * s)
     s->epoch += 1;
     NcclApi * nc = nccl_api();
     LFX_SHARD_CUDA(s, cudaMemcpyAsync(s->d_send, h->d_counts.p, sizeof(uint32_t) * 2 * n_local, cudaMemcpyDeviceToDevice, h->stream));
-    LFX_SHARD_NCCL(s, nc->AllGather(s->d_send, s->d_recv + (size_t)(s->epoch & 1u) * s->slot_words, (size_t)s->width * 2, ncclUint32, s->comm, h->stream));
+    LFX_SHARD_NCCL(s, nc->AllGather(s->d_send, s->d_recv + (size_t)(s->epoch % lfxk::SHARD_SLOTS) * s->slot_words, (size_t)s->width * 2, ncclUint32, s->comm, h->stream));
   }
   return LFX_OK;
 }

@@ -19,6 +19,11 @@ namespace lfxk
 
 constexpr int SHARD_MAX_WORLD = 64;
 constexpr int SHARD_THREADS = 1024;
+// receive slots per rank, used round robin by epoch. Three, not two: k_shard_scan_push stores the counts of epoch e + 1 into
+// the peers BEFORE it waits for their flags of epoch e, i.e. possibly while a peer one batch behind still scans its slot of
+// epoch e - 1; slot (e + 2) % 3 = (e - 1) % 3 is only written after this rank has seen that peer's flag of epoch e + 1,
+// which the peer raises after that scan.
+constexpr uint32_t SHARD_SLOTS = 3;
 
 // layout of one receive slot: [world][width][2] counts, then [world] epoch flags (all uint32)
 // (an even number of words: rows are read as 8-byte pairs in either slot)
@@ -29,20 +34,31 @@ struct ShardPeers { uint32_t * slot[SHARD_MAX_WORLD]; };   // peer p's receive s
 // this rank's counts -> block `rank` of every peer's slot, then the flag (release at system scope)
 struct ShardPushArgs { const uint32_t * counts; uint32_t n_local; ShardPeers peers; int rank, world; uint32_t width, epoch; };
 
-__device__ __forceinline__ void shard_push_body(const uint32_t * __restrict__ counts, uint32_t n_local, const ShardPeers & peers, int rank, int world,
-                                                uint32_t width, uint32_t epoch)
+// (two halves: the stores travel over NVLink while the kernel does something else - the scan of the previous exchange -
+//  and the system-scope fence in front of the flags then finds them delivered)
+__device__ __forceinline__ void shard_push_data(const uint32_t * __restrict__ counts, uint32_t n_local, const ShardPeers & peers, int rank, int world,
+                                                uint32_t width)
 {
   const uint32_t words = 2u * n_local;
   for (int p = 0; p < world; p++) {
     uint32_t * dst = peers.slot[p] + (size_t)rank * width * 2;
     for (uint32_t i = threadIdx.x; i < words; i += SHARD_THREADS) { dst[i] = counts[i]; }
   }
+}
+__device__ __forceinline__ void shard_push_flags(const ShardPeers & peers, int rank, int world, uint32_t width, uint32_t epoch)
+{
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
     uint32_t * flag = peers.slot[threadIdx.x] + (size_t)world * width * 2 + rank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(epoch) : "memory");
   }
+}
+__device__ __forceinline__ void shard_push_body(const uint32_t * __restrict__ counts, uint32_t n_local, const ShardPeers & peers, int rank, int world,
+                                                uint32_t width, uint32_t epoch)
+{
+  shard_push_data(counts, n_local, peers, rank, world, width);
+  shard_push_flags(peers, rank, world, width, epoch);
 }
 
 struct ShardScanArgs
@@ -64,9 +80,11 @@ __device__ __forceinline__ unsigned long long shard_first(unsigned long long F, 
 __device__ __forceinline__ void shard_scan_body(const ShardScanArgs & a)
 {
   __shared__ unsigned long long s_e[64], s_s[64];
+  __shared__ unsigned long long s_first[SHARD_MAX_WORLD + 1];   // first frame of every rank's block (one division each, not per frame)
   __shared__ int s_late;
   const int tid = threadIdx.x;
   if (tid == 0) { s_late = 0; }
+  if (tid <= a.world) { s_first[tid] = shard_first(a.n_frames, tid, a.world); }
   __syncthreads();
   if (a.epoch != 0 && tid < a.world) {
     const uint32_t * flag = a.slot + (size_t)a.world * a.width * 2 + tid;
@@ -91,16 +109,25 @@ __device__ __forceinline__ void shard_scan_body(const ShardScanArgs & a)
   for (unsigned long long f0 = 0; f0 < a.n_frames; f0 += (unsigned long long)PER * SHARD_THREADS) {
     uint32_t ne[PER], ns[PER];
     unsigned long long te = 0, ts = 0;
+    // owner of the thread's first frame: the largest g with first(g) <= f (binary search over the table); the next
+    // three frames are its or a neighbour's
+    int g = 0;
+    {
+      const unsigned long long f = min(f0 + (unsigned long long)tid * PER, a.n_frames - 1);
+      int lo = 0, hi = a.world - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_first[mid] <= f) { lo = mid; } else { hi = mid - 1; }
+      }
+      g = lo;
+    }
 #pragma unroll
     for (int u = 0; u < PER; u++) {
       const unsigned long long f = f0 + (unsigned long long)tid * PER + u;
       ne[u] = 0; ns[u] = 0;
       if (f < a.n_frames) {
-        // owner: the largest g with first(g) <= f; (f * G) / F is it or a neighbour of it
-        int g = (int)((f * (unsigned long long)a.world) / a.n_frames);
-        while (g + 1 < a.world && shard_first(a.n_frames, g + 1, a.world) <= f) { g++; }
-        while (g > 0 && shard_first(a.n_frames, g, a.world) > f) { g--; }
-        const unsigned long long row = f - shard_first(a.n_frames, g, a.world);
+        while (g + 1 < a.world && s_first[g + 1] <= f) { g++; }
+        const unsigned long long row = f - s_first[g];
         const uint2 v = *reinterpret_cast<const uint2 *>(a.slot + ((size_t)g * a.width + row) * 2);
         ne[u] = v.x; ns[u] = v.y;
         *reinterpret_cast<uint2 *>(a.counts_all + 2 * f) = v;
@@ -152,9 +179,10 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_push(const ShardPushArg
 // one in ONE launch at the tail of the batch
 __global__ void __launch_bounds__(SHARD_THREADS) k_shard_scan_push(const ShardScanArgs a, const ShardPushArgs p)
 {
+  shard_push_data(p.counts, p.n_local, p.peers, p.rank, p.world, p.width);   // (the slot of the OTHER parity: the scan reads the previous one)
   shard_scan_body(a);
   __syncthreads();
-  shard_push_body(p.counts, p.n_local, p.peers, p.rank, p.world, p.width, p.epoch);
+  shard_push_flags(p.peers, p.rank, p.world, p.width, p.epoch);
 }
 
 }  // namespace lfxk
