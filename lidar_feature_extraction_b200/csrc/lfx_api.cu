@@ -1870,7 +1870,7 @@ struct lfx_shard
   ncclComm_t comm = nullptr;
   int nranks = 0;
   bool p2p = false;
-  uint32_t * d_recv = nullptr;    // two receive slots (parity of the epoch)
+  uint32_t * d_recv = nullptr;    // SHARD_SLOTS receive slots, used round robin by epoch
   size_t slot_words = 0;
   uint32_t * peer_recv[lfxk::SHARD_MAX_WORLD] = {nullptr};   // peers' d_recv as mapped into this process
   bool peer_opened[lfxk::SHARD_MAX_WORLD] = {false};

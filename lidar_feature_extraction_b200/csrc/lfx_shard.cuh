@@ -29,7 +29,7 @@ constexpr uint32_t SHARD_SLOTS = 3;
 // (an even number of words: rows are read as 8-byte pairs in either slot)
 __host__ __device__ inline size_t shard_slot_words(int world, size_t width) { return ((size_t)world * width * 2 + (size_t)world + 1) & ~(size_t)1; }
 
-struct ShardPeers { uint32_t * slot[SHARD_MAX_WORLD]; };   // peer p's receive slot of the current parity, as mapped here
+struct ShardPeers { uint32_t * slot[SHARD_MAX_WORLD]; };   // peer p's receive slot of the current epoch (epoch % SHARD_SLOTS), as mapped here
 
 // this rank's counts -> block `rank` of every peer's slot, then the flag (release at system scope)
 struct ShardPushArgs { const uint32_t * counts; uint32_t n_local; ShardPeers peers; int rank, world; uint32_t width, epoch; };
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(SHARD_THREADS) k_shard_push(const ShardPushArg
 // one in ONE launch at the tail of the batch
 __global__ void __launch_bounds__(SHARD_THREADS) k_shard_scan_push(const ShardScanArgs a, const ShardPushArgs p)
 {
-  shard_push_data(p.counts, p.n_local, p.peers, p.rank, p.world, p.width);   // (the slot of the OTHER parity: the scan reads the previous one)
+  shard_push_data(p.counts, p.n_local, p.peers, p.rank, p.world, p.width);   // (slot epoch % 3: the scan below reads the previous epoch's)
   shard_scan_body(a);
   __syncthreads();
   shard_push_flags(p.peers, p.rank, p.world, p.width, p.epoch);
