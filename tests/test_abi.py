@@ -339,3 +339,28 @@ int main(int, char ** argv) {
     assert int(got["loam"][0]) == res.size
     assert abs(float(got["loam"][1]) - np.abs(J).sum()) <= 1e-6 * np.abs(J).sum() + 1e-9
     assert abs(float(got["loam"][2]) - np.abs(res).sum()) <= 1e-6 * np.abs(res).sum() + 1e-9
+
+
+def test_library_is_built_for_sm_100a_only_and_the_hot_kernels_use_the_blackwell_paths():
+    """The shipped liblfx.so holds sm_100a code and nothing else (no multi-arch fat binary, no PTX fallback path to
+    another architecture), the sector kernel fetches its points with 32-byte loads (LDG.E...256, sm_100 only) and the
+    converter stages its tiles with the TMA unit's bulk copy (UBLKCP + mbarrier transaction SYNCS)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    lib = N.LIB_PATH
+    elfs = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True, check=True).stdout.split("\n")
+    elfs = [e for e in elfs if "ELF file" in e]
+    assert elfs and all(e.strip().endswith(".sm_100a.cubin") for e in elfs), elfs
+
+    def sass(mangled):
+        return subprocess.run([cuobjdump, "-sass", "-fun", mangled, lib], capture_output=True, text=True).stdout
+
+    sector = sass("_ZN4lfxk17k_extract_sectorsILi5ELi11ELb0ELb0EEEvNS_10SectorArgsE")
+    assert sector.count("LDG.E.NA.ENL2.256") >= 11, "one 32-byte load per window position of a lane"
+    assert "DFMA" in sector and "SHFL" in sector
+    conv = sass("_ZN4lfxk9k_convertILb1EEEvNS_8ConvArgsE")
+    assert "UBLKCP" in conv and "SYNCS" in conv
