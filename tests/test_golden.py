@@ -13,7 +13,7 @@ from helpers import compare_scan, oracle_params
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
-                  if not os.path.basename(p).startswith(("convert_", "loc_")))  # converter / localization fixtures have their own tests
+                  if not os.path.basename(p).startswith(("convert_", "loc_", "envelope_")))  # converter / localization / envelope fixtures have their own tests
 PARAMSETS = {
     "default": dict(),
     "yaml": dict(padding=2, neighbor_degree_threshold=3.0, edge_threshold=50.0, max_range=1000.0),
@@ -62,3 +62,40 @@ def test_cuda_reproduces_reference_outputs(pname, diag):
     for s, (cloud, want) in enumerate(loaded):
         compare_scan(out, s, cloud, want)
     assert sum(stats["fast_rings"]) > 0 and stats["general_scans"] > 0  # both pipelines are exercised
+
+
+# ---- beyond the compiled envelope (tests/golden/make_envelope_golden.py): paddings above 15, more than 64 sectors, a
+#      9000-point ring; the CUDA side runs these on k_extract_rings_big
+ENVELOPE = sorted(glob.glob(os.path.join(HERE, "golden", "envelope_*.npz")))
+ENVELOPE_PARAMS = {
+    "default": dict(),
+    "p20": dict(padding=20),
+    "b100": dict(n_blocks=100),
+    "p33b70": dict(padding=33, n_blocks=70),
+}
+
+
+@pytest.mark.parametrize("pname", sorted(ENVELOPE_PARAMS))
+@pytest.mark.parametrize("path", ENVELOPE, ids=[os.path.basename(p)[:-4] for p in ENVELOPE])
+def test_oracle_reproduces_reference_outputs_beyond_the_envelope(oracle, path, pname):
+    from oracle import binding as ob
+
+    cloud, want = _load(path, pname)
+    got = oracle.extract_scan(cloud, ob.default_params(**ENVELOPE_PARAMS[pname]))
+    for f in ("ring_ids", "ring_sizes", "ring_skipped", "labels", "edge_idx", "surface_idx"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    assert np.array_equal(got.curvature.view(np.uint64), want.curvature.view(np.uint64)), "curvature bits"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pname", sorted(ENVELOPE_PARAMS))
+def test_cuda_reproduces_reference_outputs_beyond_the_envelope(pname):
+    from lidar_feature_extraction_b200 import FeatureExtraction, HyperParameters
+
+    assert len(ENVELOPE) >= 2
+    hp = HyperParameters(**ENVELOPE_PARAMS[pname])
+    loaded = [_load(p, pname) for p in ENVELOPE]
+    with FeatureExtraction(hp, device=0, want_sorted_src=True, want_curvature=True) as fe:
+        out = fe.extract_batch([c for c, _ in loaded])
+    for s, (cloud, want) in enumerate(loaded):
+        compare_scan(out, s, cloud, want)
